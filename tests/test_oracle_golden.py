@@ -1,0 +1,64 @@
+"""Pin the CPU oracle (oracle/emage_oracle.py) to the reference's own outputs.
+
+The golden files were produced by the UNMODIFIED reference modules
+(tests/golden/make_golden.py, run where /root/reference is visible).  These tests need
+neither the reference tree nor a GPU.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emage_oracle as O
+from oracle.weights import make_checkpoint, synth_audio
+
+CASES = ["tail11", "clip10s", "drop_tail", "short40", "seeded"]
+PARTS = ("face", "upper", "hands", "lower")
+
+
+@pytest.fixture(scope="module")
+def ckpt():
+    torch.manual_seed(0)
+    return make_checkpoint(seed=0)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference(case, ckpt, golden_dir):
+    sd, cfg, vq = ckpt
+    g = np.load(os.path.join(golden_dir, f"case_{case}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"])))
+    mm = torch.from_numpy(g["masked_motion"]) if "masked_motion" in g else None
+    mk = torch.from_numpy(g["mask"]) if "mask" in g else None
+    with torch.no_grad():
+        lat, pred = O.emage_generate(sd, cfg, vq, audio, torch.zeros(bs, 1, dtype=torch.long), mm, mk)
+    for p in PARTS:
+        # integer contract: emitted code indices are bit-exact
+        assert np.array_equal(lat["cls_" + p].argmax(-1).numpy(), g["idx_cls_" + p]), p
+        # float contract: same arithmetic, different op grouping -> fp32 rounding only
+        np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=2e-4, rtol=0)
+        np.testing.assert_allclose(lat["cls_" + p].numpy()[:, ::7], g["cls_" + p], atol=5e-4, rtol=0)
+    assert np.array_equal(pred["_index"]["face"].numpy(), g["idx_l2_face"])
+    for k in ("expression", "motion_axis_angle", "trans", "all_motion4inference"):
+        assert pred[k].shape == g[k].shape, k
+        np.testing.assert_allclose(pred[k].numpy(), g[k], atol=1e-4, rtol=0, err_msg=k)
+
+
+def test_window_plan_edge_cases():
+    # M.py:365-368: L=300 -> 4 full windows + tail of 60; L=124 -> tail dropped; L=40 -> one tail window
+    assert O.window_plan(300) == [(0, 64, 60), (60, 124, 60), (120, 184, 60), (180, 244, 60), (240, 300, 60)]
+    assert O.window_plan(124) == [(0, 64, 60), (60, 124, 60)]
+    assert O.window_plan(40) == [(0, 40, 40)]
+    assert O.window_plan(68) == [(0, 64, 60)]          # remain == 4 is not > pre -> dropped
+    assert O.window_plan(4) == []
+
+
+def test_rotation_round_trip():
+    g = torch.Generator().manual_seed(5)
+    aa = torch.randn(1000, 3, generator=g) * 0.8
+    aa = aa * torch.clamp(3.0 / aa.norm(dim=-1, keepdim=True), max=1.0)      # keep |angle| < pi
+    back = O.rot6d_to_axis_angle(O.axis_angle_to_rot6d(aa))
+    assert (back - aa).abs().max() < 1e-4
+    zero = O.rot6d_to_axis_angle(O.axis_angle_to_rot6d(torch.zeros(4, 3)))
+    assert zero.abs().max() == 0
