@@ -1,0 +1,129 @@
+/* pm_emage.h - C ABI of libpm_emage.so: the B200 (sm_100a) kernels of the EMAGE audio->motion
+ * inference hot path.
+ *
+ * The reference (PantoMatrix) has no FFI for this path: every op below is a stock torch.nn /
+ * torch.nn.functional call made from Python.  Each entry point therefore
+ * cites the reference *call site* it replaces; the Python modules in pantomatrix_b200/emage_audio
+ * (same names and signatures as /root/reference/models/emage_audio/__init__.py:1-12) are the only
+ * callers.  M.py = models/emage_audio/modeling_emage_audio.py, P.py = .../processing_emage_audio.py.
+ *
+ * Conventions
+ *   - plain pointers + explicit sizes; all pointers are DEVICE pointers unless noted
+ *   - activations are channels-last fp32: tensor (batch, rows, channels), row stride `ld*` in elements,
+ *     batch stride `*_bs` in elements (lets callers pass column slices / overlapping windows)
+ *   - `stream` is a cudaStream_t passed as void*; nothing allocates, nothing synchronises
+ *   - return 0 = ok, <0 = PM_E* argument error, >0 = cudaError_t from the launch
+ */
+#ifndef PM_EMAGE_H
+#define PM_EMAGE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+int pm_abi_version(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int pm_device_cc(void);
+
+/* ---- tap-GEMM: Conv1d (any kernel size/stride/zero padding) and Linear as one op ------------------
+ * out[b,l,n] = act( bias[n] + sum_{t<taps} sum_{c<cin} A[b, l*stride + t - pad, c] * W[t,n,c]
+ *                   + residual[b,l,n] ),  rows of A outside [0,rows_in) read as zero.
+ * W is (taps, cout, cin) fp32 (BatchNorm already folded in by the host packer).
+ * Replaces: nn.Conv1d+BatchNorm1d+LeakyReLU(+shortcut add) in BasicBlock P.py:283-294, the k=3 convs of
+ * ResBlock/VQEncoderV6/VQDecoderV5 P.py:178-261, nn.Linear everywhere (MLP P.py:322-326, projections
+ * M.py:288,293,297,304,323-325, MultiheadAttention in/out projections and FFN linear1/linear2 inside
+ * nn.Transformer{En,De}coderLayer M.py:238-250).  fp32 SIMT reference engine (exact-order fp32 FMA). */
+int pm_tapgemm_f32(const float* A, long long a_bs, int lda, int batch, int rows_in, int cin,
+                   const float* W, const float* bias, int taps, int stride, int pad,
+                   int rows_out, int cout,
+                   const float* residual, long long r_bs, int ldr,
+                   int act, float slope,
+                   float* out, long long o_bs, int ldo, void* stream);
+
+/* ---- tap-GEMM on the tcgen05 tensor cores (split-bf16 operands, fp32 TMEM accumulate) -------------
+ * Same contract as pm_tapgemm_f32 with stride == 1.  A and W are given as `nsplit` bf16 planes
+ * (x = hi + mid + lo), plane stride a_ps / w_ps elements.  `nsplit` 1 = plain bf16, 2 = bf16x3
+ * (hi*hi + hi*lo + lo*hi), 3 = bf16x6 (all products down to 2^-24).  The epilogue can write the fp32
+ * result and/or its own bf16 split planes for the next GEMM (out_f32 / out_bf16 nullable).
+ * Operands are staged by TMA (cp.async.bulk.tensor) with zero fill for the padding rows; descriptors
+ * are built on the host inside this call from the raw pointers.  */
+int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, int batch, int rows_in, int cin,
+                  const uint16_t* W, long long w_ps, int taps, int pad, int nsplit,
+                  const float* bias, int rows_out, int cout,
+                  const float* residual, long long r_bs, int ldr,
+                  int act, float slope,
+                  float* out_f32, long long o_bs, int ldo,
+                  uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
+                  void* stream);
+
+/* fp32 (batch, rows, ch) -> nsplit bf16 planes (round-to-nearest hi, then residual planes). */
+int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,
+                  uint16_t* out, long long o_ps, long long o_bs, int ldo, int nsplit, void* stream);
+
+/* ---- WavEncoder stem: first BasicBlock's conv1 and downsample conv on the raw waveform (Cin = 1) --
+ * sequence (b, w) starts at audio + b*a_bs + w*a_ws and is n_samples long; k=15, stride 5, pad 1600.
+ * Outputs are window-major: row block (w*batch + b) of (windows*batch, rows_out, cout).
+ * y1 = LeakyReLU_0.01(conv1*bn1), sc = downsample conv*bn (both BN-folded): P.py:285-291,301. */
+int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_ws, int batch, int windows, int n_samples,
+                    const float* w1, const float* b1, const float* wd, const float* bd, int cout,
+                    int ksize, int stride, int pad, int rows_out, float slope,
+                    float* y1, float* sc, void* stream);
+
+/* ---- LayerNorm(x + r) * gamma + beta over the last dim (r nullable): post-norm residual of
+ * nn.TransformerEncoderLayer / DecoderLayer (M.py:238-250), eps 1e-5.  ch must be a multiple of 128 <= 1024 */
+int pm_add_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta,
+                         float* out, long long rows, int ch, float eps, void* stream);
+
+/* ---- multi-head attention core, no masks: softmax(Q K^T / sqrt(hd)) V for Tq,Tk <= 64, hd = 192 ----
+ * Q/K/V rows are (b*T + t) with row strides ldq/ldk/ldv; head h occupies columns [h*hd,(h+1)*hd).
+ * Replaces scaled_dot_product_attention inside nn.MultiheadAttention (M.py:238-250 layers). */
+int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                     float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim, void* stream);
+
+/* ---- broadcast adds: out[b,t,:] = ((x[b,t,:] + first) + second), each of first/second chosen by code:
+ * 0 = nothing, 1 = pe[t,:] (PeriodicPositionalEncoding P.py:341-343), 2 = spk[b,:] (speaker embedding
+ * row repeated over t, M.py:285-286).  x nullable (treated as 0).  Preserves the reference's add order
+ * (M.py:291,298-299,307-308,320-322). */
+int pm_add_rows_f32(const float* x, const float* pe, const float* spk, int first, int second,
+                    float* out, int batch, int rows, int ch, void* stream);
+/* out = a + b (M.py:312,320-325) */
+int pm_add2_f32(const float* a, const float* b, float* out, long long n, void* stream);
+
+/* ---- window assembly (M.py:384-391 and 267-268 fused): builds one window's motion-encoder input.
+ * motion/mask: (batch, total_len, ch) full-sequence tensors; seed: (batch, pre, ch) decoded last frames.
+ * For frame f<pre: v = mask==0 ? motion : seed, window mask forced 0; else v = motion, m = mask.
+ * out = (m == 1) ? mask_embedding[c] : v. */
+int pm_window_input_f32(const float* motion, const float* mask, const float* seed, const float* mask_embedding,
+                        float* out, int batch, int total_len, int start, int win_len, int pre, int ch, void* stream);
+
+/* ---- VQ ------------------------------------------------------------------------------------------ */
+/* index = argmin_k ( |z|^2 + |e_k|^2 - 2 z.e_k ), first minimum wins: EmageVQVAEConv.decode_from_latent
+ * M.py:60-65, Quantizer.map2index P.py:158-164.  e_dim must be 256, n_codes a multiple of 64.
+ * e2 = precomputed |e_k|^2 (n_codes).  Writes int64 indices. */
+int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
+                     int n_codes, int e_dim, long long* index, void* stream);
+/* index = first argmax over the last dim: torch.max(F.log_softmax(x,2),2)[1], M.py:398-401 (monotone). */
+int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream);
+/* out[r,:] = codebook[index[r],:]: Quantizer.get_codebook_entry P.py:166-170 */
+int pm_gather_rows_f32(const float* codebook, const long long* index, long long rows, int ch,
+                       float* out, void* stream);
+/* |e_k|^2 per codebook row (done once at pack time) */
+int pm_row_sqnorm_f32(const float* x, int rows, int ch, float* out, void* stream);
+
+/* ---- pose composition: EmageVQModel.decode M.py:135-188 + rotation conversions P.py:6-104 ---------
+ * face (bt,106) | upper (bt,78) | hands (bt,180) | lower (bt,61) decoder outputs (any may be NULL = the
+ * reference's zero branch) -> expression (bt,100), axis_angle (bt,165), motion4inf (bt,337). */
+int pm_pose_compose_f32(const float* face, const float* upper, const float* hands, const float* lower,
+                        float* expression, float* axis_angle, float* motion4inf, long long bt, void* stream);
+
+/* ---- global translation: velocity2position P.py:107-115 as used by get_global_motion M.py:195-205 --
+ * rec (batch, t, ld) global-AE output; vel = rec[..., 54:57]; x/z integrated sequentially with dt,
+ * y copied; ref_trans (batch,3) start position. */
+int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, float dt,
+                        float* trans, int batch, int t, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,235 @@
+// Small HBM-bound kernels of the EMAGE path: WavEncoder stem, residual LayerNorm, broadcast adds,
+// window assembly.  Contracts and reference call sites: include/pm_emage.h.
+#include "pm_common.cuh"
+#include "../../include/pm_emage.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// WavEncoder stem (Cin = 1): one thread per (row, channel); both convs share the 15 input samples.
+// ---------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) wav_stem_kernel(
+    const float* __restrict__ audio, long long a_bs, long long a_ws, int batch, int n_samples,
+    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ wd,
+    const float* __restrict__ bd, int cout, int stride, int pad, int rows_out, float slope,
+    float* __restrict__ y1, float* __restrict__ sc) {
+  extern __shared__ float smem[];          // [2][cout][KS] weights, then the input span of this tile
+  const int rows_per_cta = 64;
+  float* sw1 = smem;
+  float* swd = smem + cout * KS;
+  float* sx = swd + cout * KS;             // (rows_per_cta-1)*stride + KS samples
+  const int seq = blockIdx.y;              // w*batch + b: window-major, so one window's clips are contiguous
+  const int w = seq / batch, b = seq % batch;
+  const float* __restrict__ x = audio + (long long)b * a_bs + (long long)w * a_ws;
+  const int l0 = blockIdx.x * rows_per_cta;
+  const int span = (rows_per_cta - 1) * stride + KS;
+  for (int i = threadIdx.x; i < cout * KS; i += blockDim.x) { sw1[i] = w1[i]; swd[i] = wd[i]; }
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const int s = l0 * stride - pad + i;
+    sx[i] = (s >= 0 && s < n_samples) ? x[s] : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < rows_per_cta * cout; idx += blockDim.x) {
+    const int r = idx / cout, co = idx % cout;
+    const int l = l0 + r;
+    if (l >= rows_out) break;
+    float a1 = 0.f, ad = 0.f;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const float xv = sx[r * stride + k];
+      a1 = fmaf(xv, sw1[co * KS + k], a1);
+      ad = fmaf(xv, swd[co * KS + k], ad);
+    }
+    a1 += b1[co];
+    ad += bd[co];
+    const long long o = ((long long)seq * rows_out + l) * cout + co;
+    y1[o] = a1 > 0.f ? a1 : a1 * slope;
+    sc[o] = ad;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// out = LayerNorm(x + r): one warp per row, row kept in registers, two-pass mean / variance.
+// ---------------------------------------------------------------------------------------------------
+template <int VEC>   // float4 chunks per lane: ch = VEC * 128
+__global__ void __launch_bounds__(256) add_layernorm_kernel(
+    const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ out, long long rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int CH = VEC * 128;
+  const float4* __restrict__ xr = reinterpret_cast<const float4*>(x + row * CH);
+  const float4* __restrict__ rr = r ? reinterpret_cast<const float4*>(r + row * CH) : nullptr;
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = xr[lane + 32 * i];
+    if (rr) {
+      const float4 t = rr[lane + 32 * i];
+      v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+    }
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = pm_warp_sum(s) * (1.f / CH);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(pm_warp_sum(q) * (1.f / CH) + eps);
+  const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* __restrict__ b4 = reinterpret_cast<const float4*>(beta);
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(out + row * CH);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    o4[lane + 32 * i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 pick_row(int code, const float* pe, const float* spk, int b, int t, int ch, int c4) {
+  if (code == 1) return reinterpret_cast<const float4*>(pe + (long long)t * ch)[c4];
+  if (code == 2) return reinterpret_cast<const float4*>(spk + (long long)b * ch)[c4];
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) add_rows_kernel(
+    const float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ spk,
+    int first, int second, float* __restrict__ out, int batch, int rows, int ch) {
+  const int ch4 = ch >> 2;
+  const long long total = (long long)batch * rows * ch4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % ch4);
+    const long long bt = i / ch4;
+    const int t = (int)(bt % rows), b = (int)(bt / rows);
+    float4 v = x ? reinterpret_cast<const float4*>(x)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (first) {
+      const float4 a = pick_row(first, pe, spk, b, t, ch, c4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (second) {
+      const float4 a = pick_row(second, pe, spk, b, t, ch, c4);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                   float* __restrict__ out, long long n4, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+  // scalar tail (n not a multiple of 4)
+  if (blockIdx.x == 0) {
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = a[i] + b[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) window_input_kernel(
+    const float* __restrict__ motion, const float* __restrict__ mask, const float* __restrict__ seed,
+    const float* __restrict__ mask_embedding, float* __restrict__ out,
+    int batch, int total_len, int start, int win_len, int pre, int ch) {
+  const long long total = (long long)batch * win_len * ch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ch);
+    const long long bf = i / ch;
+    const int f = (int)(bf % win_len), b = (int)(bf / win_len);
+    const long long src = ((long long)b * total_len + start + f) * ch + c;
+    float m = mask[src];
+    float v = motion[src];
+    if (f < pre) {                    // M.py:386-391
+      if (m != 0.f) v = seed[((long long)b * pre + f) * ch + c];
+      m = 0.f;
+    }
+    out[i] = (m == 1.f) ? mask_embedding[c] : v;   // M.py:267-268
+  }
+}
+
+inline int grid_for(long long work, int threads) {
+  long long g = (work + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_ws, int batch, int windows,
+                               int n_samples, const float* w1, const float* b1, const float* wd,
+                               const float* bd, int cout, int ksize, int stride, int pad, int rows_out,
+                               float slope, float* y1, float* sc, void* stream) {
+  PM_REQUIRE(audio && w1 && b1 && wd && bd && y1 && sc);
+  PM_REQUIRE(batch > 0 && windows > 0 && n_samples > 0 && cout > 0 && stride > 0 && rows_out > 0);
+  if (ksize != 15) return PM_EUNSUPPORTED;
+  PM_REQUIRE((long long)batch * windows <= 65535);
+  const int span = 63 * stride + ksize;
+  const size_t smem = (size_t)(2 * cout * ksize + span) * sizeof(float);
+  PM_REQUIRE(smem <= 48 * 1024);
+  dim3 grid(pm_cdiv(rows_out, 64), batch * windows);
+  wav_stem_kernel<15><<<grid, 256, smem, (cudaStream_t)stream>>>(
+      audio, a_bs, a_ws, batch, n_samples, w1, b1, wd, bd, cout, stride, pad, rows_out, slope, y1, sc);
+  PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_add_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta,
+                                    float* out, long long rows, int ch, float eps, void* stream) {
+  PM_REQUIRE(x && gamma && beta && out && rows >= 0);
+  if (rows == 0) return PM_OK;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ch) {
+    case 256: add_layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
+    case 512: add_layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
+    case 768: add_layernorm_kernel<6><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
+    case 1024: add_layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
+    default: return PM_EUNSUPPORTED;
+  }
+  PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_add_rows_f32(const float* x, const float* pe, const float* spk, int first, int second,
+                               float* out, int batch, int rows, int ch, void* stream) {
+  PM_REQUIRE(out && batch >= 0 && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_REQUIRE(first >= 0 && first <= 2 && second >= 0 && second <= 2);
+  PM_REQUIRE((first != 1 && second != 1) || pe);
+  PM_REQUIRE((first != 2 && second != 2) || spk);
+  const long long total = (long long)batch * rows * (ch >> 2);
+  if (total == 0) return PM_OK;
+  add_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, spk, first, second, out,
+                                                                        batch, rows, ch);
+  PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_add2_f32(const float* a, const float* b, float* out, long long n, void* stream) {
+  PM_REQUIRE(a && b && out && n >= 0);
+  if (n == 0) return PM_OK;
+  add2_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n);
+  PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_window_input_f32(const float* motion, const float* mask, const float* seed,
+                                   const float* mask_embedding, float* out, int batch, int total_len,
+                                   int start, int win_len, int pre, int ch, void* stream) {
+  PM_REQUIRE(motion && mask && mask_embedding && out && (seed || pre == 0));
+  PM_REQUIRE(batch >= 0 && win_len >= 0 && start >= 0 && start + win_len <= total_len && pre >= 0 && ch > 0);
+  const long long total = (long long)batch * win_len * ch;
+  if (total == 0) return PM_OK;
+  window_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch);
+  PM_LAUNCH_CHECK();
+}

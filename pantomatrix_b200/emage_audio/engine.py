@@ -1,0 +1,406 @@
+"""Execution engine of the EMAGE hot path: packed device weights + the kernel schedule.
+
+Host logic only (Python, like the reference); every arithmetic op is a libpm_emage.so kernel reached
+through pantomatrix_b200.ops.  Citations: M.py = /root/reference/models/emage_audio/modeling_emage_audio.py,
+P.py = .../processing_emage_audio.py.
+
+Schedule differences from the reference that do not change results beyond fp32 rounding:
+  * BatchNorm (eval) is folded into the preceding conv at pack time (P.py:285-291).
+  * Everything that depends only on audio is hoisted out of the sequential window loop and batched over
+    all windows of all clips: both WavEncoders, audio_body_motion_proj, the audio half of
+    audio_face_motion_proj and the cross-attention K/V projections of the 8 audio_motion_cross_attn
+    layers.  Each window still sees its own zero-padded audio slice, as in the
+    reference (M.py:393-396), so window-local conv results are reproduced exactly.
+  * In-loop VQ decodes only produce the seed frames (M.py:418): the conv decoders are run on the last
+    `SEED_DECODE_FRAMES` frames, which covers their receptive field (+-9 frames for vae_layer=4).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+PARTS = ("face", "upper", "hands", "lower")
+# WavEncoder geometry P.py:300-307: (stride, first-conv padding, has downsample branch)
+WAV_BLOCKS = ((5, 1600, True), (6, 0, True), (1, 7, False), (6, 0, True), (1, 7, False), (3, 0, True))
+SEED_DECODE_FRAMES = 16
+NHEAD = 4
+
+
+def _taps(w: torch.Tensor) -> torch.Tensor:
+    """conv weight (cout, cin, k) -> tap-major (k, cout, cin)."""
+    return w.permute(2, 0, 1).contiguous()
+
+
+def _fold_bn(sd, conv, bn, eps=1e-5):
+    w, b = sd[conv + ".weight"].double(), sd[conv + ".bias"].double()
+    s = sd[bn + ".weight"].double() / torch.sqrt(sd[bn + ".running_var"].double() + eps)
+    return (w * s[:, None, None]).float(), ((b - sd[bn + ".running_mean"].double()) * s + sd[bn + ".bias"].double()).float()
+
+
+def wav_out_len(n: int) -> int:
+    """Frames a WavEncoder emits for n samples (P.py:300-307 conv arithmetic)."""
+    length = n
+    for stride, pad, _ in WAV_BLOCKS:
+        length = (length + 2 * pad - 15) // stride + 1
+    return length
+
+
+class _Conv:
+    __slots__ = ("w", "b", "stride", "pad")
+
+    def __init__(self, w, b, stride=1, pad=0):
+        self.w, self.b, self.stride, self.pad = w, b, stride, pad
+
+    def __call__(self, x, act=ops.ACT_NONE, slope=0.0, residual=None, out=None):
+        return ops.tapgemm(x, self.w, self.b, stride=self.stride, pad=self.pad, act=act, slope=slope,
+                           residual=residual, out=out)
+
+
+class _Linear(_Conv):
+    def __init__(self, sd, prefix=None, w=None, b=None):
+        if prefix is not None:
+            w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+        super().__init__(w.contiguous().unsqueeze(0), None if b is None else b.contiguous())
+
+
+class _MLP:
+    """P.py:316-326."""
+
+    def __init__(self, sd, p):
+        self.fc1, self.fc2 = _Linear(sd, p + ".fc1"), _Linear(sd, p + ".fc2")
+
+    def __call__(self, x, out=None):
+        return self.fc2(self.fc1(x, act=ops.ACT_LEAKY, slope=0.1), out=out)
+
+
+class _ConvStack:
+    """k=3 conv stacks: VQEncoderV5/V6 (P.py:189-235) and VQDecoderV5 (P.py:237-261)."""
+
+    def __init__(self, sd, prefix, kind, n_layer):
+        c = lambda i, sub="": _Conv(_taps(sd[f"{prefix}.main.{i}{sub}.weight"]), sd[f"{prefix}.main.{i}{sub}.bias"].contiguous(), 1, 1)
+        self.steps = []           # ("conv", conv, act) | ("res", conv_a, conv_b)
+        if kind == "encoder":
+            for i in range(n_layer):
+                self.steps.append(("conv", c(3 * i), True))
+                self.steps.append(("res", c(3 * i + 2, ".model.0"), c(3 * i + 2, ".model.2")))
+        else:
+            self.steps.append(("res", c(0, ".model.0"), c(0, ".model.2")))
+            self.steps.append(("res", c(1, ".model.0"), c(1, ".model.2")))
+            for i in range(n_layer):
+                self.steps.append(("conv", c(2 + 2 * i), True))
+            self.steps.append(("conv", c(2 + 2 * n_layer), False))
+
+    def __call__(self, x):
+        for step in self.steps:
+            if step[0] == "conv":
+                x = step[1](x, act=ops.ACT_LEAKY if step[2] else ops.ACT_NONE, slope=0.2)
+            else:
+                x = step[2](step[1](x, act=ops.ACT_LEAKY, slope=0.2), residual=x)
+        return x
+
+
+class _WavEncoder:
+    """P.py:263-314 with BatchNorm folded; input is a set of (clip, window) waveform slices."""
+
+    def __init__(self, sd, p):
+        self.blocks = []
+        for i, (stride, pad, has_ds) in enumerate(WAV_BLOCKS):
+            q = f"{p}.feat_extractor.{i}"
+            w1, b1 = _fold_bn(sd, q + ".conv1", q + ".bn1")
+            w2, b2 = _fold_bn(sd, q + ".conv2", q + ".bn2")
+            ds = _fold_bn(sd, q + ".downsample.0", q + ".downsample.1") if has_ds else None
+            if i == 0:
+                self.stem = (w1.reshape(w1.shape[0], -1).contiguous(), b1.contiguous(),
+                             ds[0].reshape(ds[0].shape[0], -1).contiguous(), ds[1].contiguous(), stride, pad)
+                self.blocks.append((None, _Conv(_taps(w2), b2.contiguous(), 1, 7), None))
+            else:
+                self.blocks.append((_Conv(_taps(w1), b1.contiguous(), stride, pad), _Conv(_taps(w2), b2.contiguous(), 1, 7),
+                                    _Conv(_taps(ds[0]), ds[1].contiguous(), stride, pad) if ds else None))
+
+    def __call__(self, audio, offset, a_ws, windows, n_samples):
+        """audio (bs, n) contiguous; returns (windows*bs, frames, out_dim), window-major."""
+        bs, n = audio.shape
+        w1, b1, wd, bd, stride, pad = self.stem
+        y, sc = ops.wav_stem(audio, n, a_ws, bs, windows, n_samples, w1, b1, wd, bd, stride=stride, pad=pad,
+                             slope=0.01, offset=offset)
+        x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc)
+        for conv1, conv2, ds in self.blocks[1:]:
+            y = conv1(x, act=ops.ACT_LEAKY, slope=0.01)
+            sc = ds(x) if ds is not None else x
+            x = conv2(y, act=ops.ACT_LEAKY, slope=0.01, residual=sc)
+        return x
+
+
+class _Attn:
+    """nn.MultiheadAttention weights (packed in_proj (3E,E): Q | K | V rows)."""
+
+    def __init__(self, sd, p, E):
+        w, b = sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"]
+        self.qkv = _Linear(None, w=w, b=b)
+        self.q = _Linear(None, w=w[:E], b=b[:E])
+        self.kv = _Linear(None, w=w[E:], b=b[E:])
+        self.out = _Linear(sd, p + ".out_proj")
+        self.E = E
+
+
+class _Layer:
+    """Post-norm nn.TransformerEncoderLayer / DecoderLayer (ReLU FFN), M.py:238-250."""
+
+    def __init__(self, sd, p, E, cross):
+        self.E = E
+        self.sa = _Attn(sd, p + ".self_attn", E)
+        self.ca = _Attn(sd, p + ".multihead_attn", E) if cross else None
+        self.l1, self.l2 = _Linear(sd, p + ".linear1"), _Linear(sd, p + ".linear2")
+        n = 3 if cross else 2
+        self.norms = [(sd[f"{p}.norm{i + 1}.weight"].contiguous(), sd[f"{p}.norm{i + 1}.bias"].contiguous()) for i in range(n)]
+
+    def project_memory(self, mem):
+        """K|V projection of a cross-attention memory (bs, tk, E) -> (bs, tk, 2E)."""
+        return self.ca.kv(mem)
+
+    def __call__(self, x, mem_kv=None):
+        bs, t, E = x.shape
+        hd = E // NHEAD
+        qkv = self.sa.qkv(x).view(bs * t, 3 * E)
+        att = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], bs, NHEAD, t, t, hd).view(bs, t, E)
+        x = ops.add_layernorm(self.sa.out(att, residual=x), None, *self.norms[0])
+        k = 1
+        if self.ca is not None:
+            tk = mem_kv.shape[1]
+            assert mem_kv.is_contiguous()
+            kv = mem_kv.view(bs * tk, 2 * E)
+            q = self.ca.q(x).view(bs * t, E)
+            att = ops.attention(q, kv[:, :E], kv[:, E:], bs, NHEAD, t, tk, hd).view(bs, t, E)
+            x = ops.add_layernorm(self.ca.out(att, residual=x), None, *self.norms[1])
+            k = 2
+        h = self.l1(x, act=ops.ACT_RELU)
+        return ops.add_layernorm(self.l2(h, residual=x), None, *self.norms[k])
+
+
+class EmageEngine:
+    """Packed EmageAudioModel (M.py:208-263)."""
+
+    def __init__(self, sd, cfg):
+        self.cfg = cfg
+        E = self.E = int(cfg["hidden_size"])
+        self.device = sd["mask_embedding"].device        # CUDA: enforced by the owning module and by ops._chk
+        self.wav_face = _WavEncoder(sd, "audio_encoder_face")
+        self.wav_body = _WavEncoder(sd, "audio_encoder_body")
+        self.motion_encoder = _ConvStack(sd, "motion_encoder", "encoder", 3)            # M.py:227-231
+        self.hint_face, self.hint_body = _MLP(sd, "bodyhints_face"), _MLP(sd, "bodyhints_body")
+        af = int(cfg["audio_f"])
+        wf, bf = sd["audio_face_motion_proj.weight"], sd["audio_face_motion_proj.bias"]
+        self.face_mem_audio = _Linear(None, w=wf[:, :af], b=bf)       # audio half of the 512->768 proj (hoisted)
+        self.face_mem_hint = _Linear(None, w=wf[:, af:], b=None)      # motion-hint half (in loop, accumulates)
+        self.body_mem = _Linear(sd, "audio_body_motion_proj")
+        self.moton_proj = _Linear(sd, "moton_proj")
+        self.spk_face = sd["speaker_embedding_face.weight"].contiguous()
+        self.spk_body = sd["speaker_embedding_body.weight"].contiguous()
+        self.pe = sd["position_embeddings.pe"][0].contiguous()                         # (128, E)
+        self.mask_embedding = sd["mask_embedding"].reshape(-1).contiguous()
+        self.self_enc = _Layer(sd, "motion_self_encoder.layers.0", E, cross=False)
+        self.cross = [_Layer(sd, f"audio_motion_cross_attn.layers.{i}", E, True) for i in range(8)]
+        self.face_dec = [_Layer(sd, f"face_motion_decoder.layers.{i}", E, True) for i in range(4)]
+        self.refine = {p: _Layer(sd, f"body_motion_decoder_{p}.layers.0", E, True) for p in PARTS[1:]}
+        self.to_latent = {p: _MLP(sd, "motion2latent_" + p) for p in PARTS[1:]}
+        self.out_proj = {p: _Linear(sd, "motion_out_proj_" + p) for p in PARTS[1:]}
+        self.out_proj["face"] = _Linear(sd, "face_out_proj")
+        self.cls = {p: _MLP(sd, "motion_cls_" + p) for p in PARTS[1:]}
+        self.cls["face"] = _MLP(sd, "face_cls")
+
+    # ------------------------------------------------------------------------------------------------
+    def audio_phase(self, audio, offset, a_ws, windows, n_samples, t):
+        """Everything that depends on audio only, for `windows` equally long slices per clip.
+        Returns window-major tensors: face memory audio part (w*bs, t, E), body cross-attn K|V of the
+        8 layers (list of (w*bs, tk, 2E))."""
+        a_face = self.wav_face(audio, offset, a_ws, windows, n_samples)
+        a_body = self.wav_body(audio, offset, a_ws, windows, n_samples)
+        if a_face.shape[1] < t:
+            raise ValueError(f"audio slice yields {a_face.shape[1]} frames < {t} motion frames")
+        a_face = a_face[:, :t]                     # M.py:278-281 (the body stream is never truncated)
+        mem_face = self.face_mem_audio(a_face)
+        mem_body = self.body_mem(a_body)
+        kv = [layer.project_memory(mem_body) for layer in self.cross]
+        return mem_face, kv
+
+    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body):
+        """One window of EmageAudioModel.forward (M.py:265-341) given the hoisted audio tensors.
+        win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows)."""
+        bs, t, _ = win_in.shape
+        E = self.E
+        spk_f, spk_b = speaker_id_rows
+        hint = self.motion_encoder(win_in)                                              # M.py:271
+        hint_body, hint_face = self.hint_body(hint), self.hint_face(hint)
+        out = {}
+        # face branch, M.py:288-294
+        mem_f = self.face_mem_hint(hint_face, residual=mem_face_audio)
+        x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
+        for layer in self.face_dec:
+            x = layer(x, layer.project_memory(mem_f))
+        out["rec_face"] = self.out_proj["face"](x)
+        out["cls_face"] = self.cls["face"](out["rec_face"])
+        # body branch, M.py:297-330
+        x = ops.add_rows(self.moton_proj(hint_body), self.pe, spk_b, ops.ROW_PE, ops.ROW_SPK, bs, t, E)
+        fea = self.self_enc(x)
+        fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
+        x = fea
+        for layer, kv in zip(self.cross, kv_body):
+            x = layer(x, kv)
+        fea = ops.add2(fea, x)
+        lat = {p: self.to_latent[p](fea) for p in PARTS[1:]}
+        others = {"upper": ("hands", "lower"), "hands": ("upper", "lower"), "lower": ("upper", "hands")}
+        for p in PARTS[1:]:
+            a, b = others[p]
+            layer = self.refine[p]
+            tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E)
+            refine = layer(tgt, layer.project_memory(ops.add2(lat[a], lat[b])))
+            out["rec_" + p] = self.out_proj[p](ops.add2(lat[p], refine))
+            out["cls_" + p] = self.cls[p](out["rec_" + p])
+        return out
+
+    def speaker_rows(self, speaker_id):
+        """nn.Embedding lookup of the (bs,1) speaker ids (M.py:285-286): pure row gather."""
+        ids = speaker_id.reshape(-1).to(torch.int64).contiguous()
+        return ops.gather_rows(self.spk_face, ids), ops.gather_rows(self.spk_body, ids)
+
+
+class VQEngine:
+    """Packed EmageVQModel: four EmageVQVAEConv decoders/codebooks + the global EmageVAEConv
+    (M.py:19-205)."""
+
+    DIMS = {"face": 106, "upper": 78, "hands": 180, "lower": 61}
+
+    def __init__(self, sds, cfgs):
+        self.codebook, self.e2, self.decoder, self.encoder = {}, {}, {}, {}
+        for p in PARTS:
+            sd, cfg = sds[p], cfgs[p]
+            self.codebook[p] = sd["quantizer.embedding.weight"].contiguous()
+            self.e2[p] = ops.row_sqnorm(self.codebook[p])
+            self.decoder[p] = _ConvStack(sd, "decoder", "decoder", int(cfg["vae_layer"]))
+            self._enc_args = None
+        self.has_global = "global" in sds and sds["global"] is not None
+        if self.has_global:
+            n = int(cfgs["global"]["vae_layer"])
+            self.global_enc = _ConvStack(sds["global"], "encoder", "encoder", n)
+            self.global_dec = _ConvStack(sds["global"], "decoder", "decoder", n)
+        self.device = self.codebook["face"].device
+
+    def part_decode(self, p, index=None, latent=None):
+        """EmageVQVAEConv.decode / decode_from_latent (M.py:56-70) -> (pose features, indices)."""
+        if index is None:
+            index = ops.l2_argmin(latent.contiguous(), self.codebook[p], self.e2[p])
+        return self.decoder[p](ops.gather_rows(self.codebook[p], index.contiguous())), index
+
+    def decode(self, index, latent, get_global_motion=False, ref_trans=None):
+        """index/latent: dicts part -> tensor or None.  Returns the reference's 4-key dict (M.py:193)."""
+        shape = next(t.shape[:2] for t in list(index.values()) + list(latent.values()) if t is not None)
+        bs, t = int(shape[0]), int(shape[1])
+        feats = {}
+        for p in PARTS:
+            if index.get(p) is not None or latent.get(p) is not None:
+                feats[p], _ = self.part_decode(p, index.get(p), latent.get(p))
+        expression, aa, m4 = ops.pose_compose(feats.get("face"), feats.get("upper"), feats.get("hands"),
+                                              feats.get("lower"), bs, t, self.device)
+        trans = None
+        if get_global_motion:
+            lower_mix = feats.get("lower")
+            if lower_mix is None:                   # M.py:174-178: identity rotations + zero trans/contact
+                lower_mix = torch.zeros(bs, t, 61, device=self.device)
+                lower_mix[:, :, 0:54:6] = 1.0
+                lower_mix[:, :, 4:54:6] = 1.0
+            trans = self.global_motion(lower_mix, ref_trans)
+        return dict(expression=expression, all_motion4inference=m4, motion_axis_angle=aa, trans=trans)
+
+    def global_motion(self, lower_mix, ref_trans):
+        """M.py:195-205."""
+        rec = self.global_dec(self.global_enc(lower_mix))
+        bs = rec.shape[0]
+        if ref_trans.dim() == 2:                    # (n,3) -> every clip starts at row 0 (M.py:198-201)
+            ref = ref_trans[0:1].expand(bs, 3)
+        else:
+            ref = ref_trans[:, 0]
+        ref = ref.to(device=rec.device, dtype=torch.float32).contiguous()
+        return ops.global_trans(rec, ref, 1 / 30)
+
+
+def select_inputs(cfg, out, idx):
+    """M.py:403-410 / T.py:34-42: latent for a part iff l?>0 and c?==0, class index iff c?>0."""
+    index, latent = {}, {}
+    for p, lk, ck in (("face", "lf", "cf"), ("upper", "lu", "cu"), ("hands", "lh", "ch"), ("lower", "ll", "cl")):
+        latent[p] = out["rec_" + p] if cfg[lk] > 0 and cfg[ck] == 0 else None
+        index[p] = idx[p] if cfg[ck] > 0 else None
+    return index, latent
+
+
+def window_plan(total_len, window, pre):
+    """M.py:365-368,380-382,428-430 -> [(start, end, frames kept)]."""
+    step = window - pre
+    rounds, remain = (total_len - pre) // step, (total_len - pre) % step
+    plan = [(i * step, i * step + window, step) for i in range(rounds)]
+    if remain > pre:
+        plan.append((rounds * step, rounds * step + pre + remain, pre + remain))
+    return plan
+
+
+def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_motion=None, mask=None):
+    """EmageAudioModel.inference (M.py:343-490)."""
+    cfg = engine.cfg
+    dev = engine.device
+    audio = audio.to(device=dev, dtype=torch.float32).contiguous()
+    bs, n = audio.shape
+    length = n * 30 // 16000                                                             # M.py:345
+    window, pre = int(cfg["pose_length"]), int(cfg["seed_frames"])
+    ch = int(cfg["pose_dims"]) + 7
+    # default motion = identity rotations (rot6d of zero axis-angle is [1,0,0,0,1,0]) + zero trans/contact
+    motion = torch.zeros(bs, length, ch, device=dev)
+    motion[:, :, 0:ch - 7:6] = 1.0
+    motion[:, :, 4:ch - 7:6] = 1.0
+    if masked_motion is not None:
+        motion[:, :masked_motion.shape[1]] = masked_motion.to(dev)
+    full_mask = torch.ones(bs, length, ch, device=dev)
+    if mask is not None:
+        full_mask[:, :mask.shape[1]] = mask.to(dev)
+    plan = window_plan(length, window, pre)
+    spf = 16000 // 30                                                                    # 533, M.py:393
+    if not plan:
+        raise RuntimeError("audio too short: no window to generate (reference torch.cat of an empty list fails too)")
+    spk = engine.speaker_rows(speaker_id.to(dev))
+
+    # ---- hoisted audio phase: full windows as one batch, tail window separately ----
+    n_full = sum(1 for s, e, _ in plan if e - s == window)
+    groups = []
+    if n_full:
+        groups.append((0, n_full, window))
+    if len(plan) > n_full:
+        groups.append((n_full, 1, plan[-1][1] - plan[-1][0]))
+    hoisted = {}
+    for first, count, t in groups:
+        s0 = plan[first][0]
+        mem_face, kv = engine.audio_phase(audio, s0 * spf, (window - pre) * spf, count, t * spf, t)
+        E = engine.E
+        mem_face = mem_face.view(count, bs, t, E)                 # window-major: each window is contiguous
+        kv = [k.view(count, bs, k.shape[1], 2 * E) for k in kv]
+        for j in range(count):
+            hoisted[first + j] = (mem_face[j], [k[j] for k in kv])
+
+    out_len = sum(k for _, _, k in plan)
+    acc = {k + p: torch.empty(bs, out_len, 256, device=dev) for k in ("rec_", "cls_") for p in PARTS}
+    seed = motion[:, :pre].contiguous()                                                  # M.py:379
+    off = 0
+    for wi, (s, e, keep) in enumerate(plan):
+        t = e - s
+        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre)
+        mem_face, kv = hoisted[wi]
+        out = engine.window(win_in, spk, mem_face, kv)
+        for k in acc:
+            acc[k][:, off:off + keep].copy_(out[k][:, :keep])                           # M.py:419-426,463-470
+        off += keep
+        if wi + 1 < len(plan):                                                           # seed for the next window
+            nd = min(t, SEED_DECODE_FRAMES)
+            tail = {k: v[:, t - nd:].contiguous() for k, v in out.items()}
+            idx = {p: ops.row_argmax(tail["cls_" + p]) for p in PARTS}                   # M.py:398-401
+            index, latent = select_inputs(cfg, tail, idx)
+            dec = vq.decode(index, latent)
+            seed = dec["all_motion4inference"][:, nd - pre:].contiguous()                # M.py:418
+    return acc

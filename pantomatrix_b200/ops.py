@@ -1,0 +1,206 @@
+"""Thin torch-tensor wrappers over the C ABI (include/pm_emage.h).
+
+torch is used only for device memory (torch.empty), the current CUDA stream and tensor views; every
+arithmetic op of the hot path is a kernel of libpm_emage.so.  All functions require CUDA tensors and
+raise (PmError) on any failure - there is no fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
+
+# number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _lib.PmError("pantomatrix_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.PmError(f"expected {dtype}, got {t.dtype}")
+    if t.dim() and t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise _lib.PmError("innermost dimension must be contiguous")
+    return t
+
+
+def _call(name, *args):
+    global launch_count
+    launch_count += 1
+    _lib.call(name, *args)
+
+
+def _bs_ld(t: torch.Tensor):
+    """(batch stride, row stride) in elements of a (batch, rows, ch) view."""
+    return (t.stride(0) if t.shape[0] > 1 else t.shape[1] * t.stride(1)), t.stride(1)
+
+
+def tapgemm(a, w, bias, *, rows_out=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, residual=None, out=None):
+    """out[b,l,:] = act(bias + sum_t A[b, l*stride+t-pad, :] @ W[t].T + residual[b,l,:]).
+
+    a: (batch, rows_in, cin); w: (taps, cout, cin) contiguous; returns (batch, rows_out, cout)."""
+    _chk(a), _chk(w)
+    batch, rows_in, cin = a.shape
+    taps, cout, cin_w = w.shape
+    assert cin_w == cin and w.is_contiguous(), (w.shape, a.shape)
+    if rows_out is None:
+        rows_out = (rows_in + 2 * pad - taps) // stride + 1
+    if out is None:
+        out = torch.empty(batch, rows_out, cout, device=a.device, dtype=torch.float32)
+    else:
+        assert out.shape == (batch, rows_out, cout), (out.shape, (batch, rows_out, cout))
+    _chk(out)
+    if residual is not None:
+        _chk(residual)
+        assert residual.shape == out.shape
+    # a Linear (taps == 1, no padding) over contiguous batches is one tall matrix: better tile use
+    if (taps == 1 and pad == 0 and stride == 1 and batch > 1 and a.stride(0) == rows_in * a.stride(1)
+            and out.stride(0) == rows_out * out.stride(1)
+            and (residual is None or residual.stride(0) == rows_out * residual.stride(1))):
+        a = a.reshape(1, batch * rows_in, cin) if a.is_contiguous() else a.as_strided(
+            (1, batch * rows_in, cin), (0, a.stride(1), 1), a.storage_offset())
+        flat = lambda t: t.as_strided((1, batch * rows_out, cout), (0, t.stride(1), 1), t.storage_offset())
+        out_v = flat(out)
+        res_v = flat(residual) if residual is not None else None
+        batch_k, rows_in_k, rows_out_k = 1, batch * rows_in, batch * rows_out
+    else:
+        out_v, res_v, batch_k, rows_in_k, rows_out_k = out, residual, batch, rows_in, rows_out
+    a_bs, lda = _bs_ld(a)
+    o_bs, ldo = _bs_ld(out_v)
+    r_bs, ldr = _bs_ld(res_v) if res_v is not None else (0, 0)
+    _call("pm_tapgemm_f32", a.data_ptr(), a_bs, lda, batch_k, rows_in_k, cin,
+          w.data_ptr(), _ptr(bias), taps, stride, pad, rows_out_k, cout,
+          _ptr(res_v), r_bs, ldr, act, float(slope), out_v.data_ptr(), o_bs, ldo, _stream())
+    return out
+
+
+def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0):
+    """First WavEncoder block's two convolutions on the raw waveform.  `audio` is the flat (bs, n)
+    tensor; sequence (b, w) starts at element offset + b*a_bs + w*a_ws and is n_samples long."""
+    _chk(audio)
+    cout, ks = w1.shape
+    rows_out = (n_samples + 2 * pad - ks) // stride + 1
+    y1 = torch.empty(batch * windows, rows_out, cout, device=audio.device, dtype=torch.float32)
+    sc = torch.empty_like(y1)
+    _call("pm_wav_stem_f32", audio.data_ptr() + 4 * offset, a_bs, a_ws, batch, windows, n_samples,
+          w1.data_ptr(), b1.data_ptr(), wd.data_ptr(), bd.data_ptr(), cout, ks, stride, pad, rows_out,
+          float(slope), y1.data_ptr(), sc.data_ptr(), _stream())
+    return y1, sc
+
+
+def add_layernorm(x, r, gamma, beta, eps=1e-5, out=None):
+    _chk(x)
+    assert x.is_contiguous() and (r is None or (r.is_contiguous() and r.shape == x.shape))
+    ch = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    _call("pm_add_layernorm_f32", x.data_ptr(), _ptr(r), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+          x.numel() // ch, ch, float(eps), _stream())
+    return out
+
+
+def attention(q, k, v, batch, heads, tq, tk, head_dim):
+    """q: (batch*tq, >=heads*head_dim) view, k/v: (batch*tk, ...) views (column slices allowed)."""
+    for t in (q, k, v):
+        _chk(t)
+    out = torch.empty(batch * tq, heads * head_dim, device=q.device, dtype=torch.float32)
+    _call("pm_attention_f32", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+          out.data_ptr(), out.stride(0), batch, heads, tq, tk, head_dim, _stream())
+    return out
+
+
+def add_rows(x, pe, spk, first, second, batch, rows, ch):
+    out = torch.empty(batch, rows, ch, device=(pe if pe is not None else spk).device, dtype=torch.float32)
+    if x is not None:
+        _chk(x)
+        assert x.is_contiguous() and x.numel() == out.numel()
+    _call("pm_add_rows_f32", _ptr(x), _ptr(pe), _ptr(spk), first, second, out.data_ptr(), batch, rows, ch, _stream())
+    return out
+
+
+def add2(a, b):
+    _chk(a), _chk(b)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a)
+    _call("pm_add2_f32", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
+    return out
+
+
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre):
+    _chk(motion), _chk(mask), _chk(seed)
+    assert motion.is_contiguous() and mask.is_contiguous() and seed.is_contiguous()
+    batch, total_len, ch = motion.shape
+    assert mask.shape == motion.shape and seed.shape == (batch, pre, ch)
+    out = torch.empty(batch, win_len, ch, device=motion.device, dtype=torch.float32)
+    _call("pm_window_input_f32", motion.data_ptr(), mask.data_ptr(), seed.data_ptr(), mask_embedding.data_ptr(),
+          out.data_ptr(), batch, total_len, start, win_len, pre, ch, _stream())
+    return out
+
+
+def l2_argmin(z, codebook, e2):
+    _chk(z), _chk(codebook), _chk(e2)
+    assert z.is_contiguous() and codebook.is_contiguous()
+    rows = z.numel() // z.shape[-1]
+    idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
+    _call("pm_l2_argmin_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), codebook.shape[0],
+          codebook.shape[1], idx.data_ptr(), _stream())
+    return idx
+
+
+def row_argmax(x):
+    _chk(x)
+    assert x.is_contiguous()
+    ch = x.shape[-1]
+    idx = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int64)
+    _call("pm_row_argmax_f32", x.data_ptr(), x.numel() // ch, ch, ch, idx.data_ptr(), _stream())
+    return idx
+
+
+def gather_rows(codebook, index):
+    _chk(codebook), _chk(index, torch.int64)
+    assert index.is_contiguous()
+    out = torch.empty(*index.shape, codebook.shape[1], device=codebook.device, dtype=torch.float32)
+    _call("pm_gather_rows_f32", codebook.data_ptr(), index.data_ptr(), index.numel(), codebook.shape[1],
+          out.data_ptr(), _stream())
+    return out
+
+
+def row_sqnorm(x):
+    _chk(x)
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    _call("pm_row_sqnorm_f32", x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), _stream())
+    return out
+
+
+def pose_compose(face, upper, hands, lower, bs, t, device):
+    for ten, dim in ((face, 106), (upper, 78), (hands, 180), (lower, 61)):
+        if ten is not None:
+            _chk(ten)
+            assert ten.is_contiguous() and ten.shape == (bs, t, dim), (ten.shape, dim)
+    expression = torch.empty(bs, t, 100, device=device, dtype=torch.float32)
+    axis_angle = torch.empty(bs, t, 165, device=device, dtype=torch.float32)
+    motion4inf = torch.empty(bs, t, 337, device=device, dtype=torch.float32)
+    _call("pm_pose_compose_f32", _ptr(face), _ptr(upper), _ptr(hands), _ptr(lower), expression.data_ptr(),
+          axis_angle.data_ptr(), motion4inf.data_ptr(), bs * t, _stream())
+    return expression, axis_angle, motion4inf
+
+
+def global_trans(rec, ref_trans, dt, vel_off=54):
+    _chk(rec), _chk(ref_trans)
+    assert rec.is_contiguous() and ref_trans.is_contiguous()
+    bs, t, ld = rec.shape
+    assert ref_trans.shape == (bs, 3)
+    trans = torch.empty(bs, t, 3, device=rec.device, dtype=torch.float32)
+    _call("pm_global_trans_f32", rec.data_ptr(), ld, vel_off, ref_trans.data_ptr(), float(dt), trans.data_ptr(),
+          bs, t, _stream())
+    return trans

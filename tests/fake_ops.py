@@ -1,0 +1,118 @@
+"""A torch-CPU stand-in for pantomatrix_b200.ops, for HOST-LOGIC tests only (tests/test_host_logic.py).
+
+The build container has no GPU.  To exercise the Python scheduling code of the product (window plan,
+audio hoisting, weight packing / BatchNorm folding, seed decode, strides and views) without a device, the
+kernel wrappers are replaced by these restatements of each kernel's contract (include/pm_emage.h).  This
+file lives under tests/ and is never importable from the product package."""
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
+launch_count = 0
+
+
+def _act(v, act, slope):
+    return F.relu(v) if act == ACT_RELU else F.leaky_relu(v, slope) if act == ACT_LEAKY else v
+
+
+def tapgemm(a, w, bias, *, rows_out=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, residual=None, out=None):
+    y = F.conv1d(a.transpose(1, 2), w.permute(1, 2, 0), bias, stride=stride, padding=pad).transpose(1, 2)
+    if rows_out is not None:
+        y = y[:, :rows_out]
+    if residual is not None:
+        y = y + residual
+    y = _act(y, act, slope)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y.contiguous()
+
+
+def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0):
+    flat = audio.reshape(-1)
+    seqs = torch.stack([flat[offset + b * a_bs + w * a_ws: offset + b * a_bs + w * a_ws + n_samples]
+                        for w in range(windows) for b in range(batch)])            # window-major
+    x = seqs.unsqueeze(1)
+    y1 = F.leaky_relu(F.conv1d(x, w1.unsqueeze(1), b1, stride=stride, padding=pad), slope).transpose(1, 2)
+    sc = F.conv1d(x, wd.unsqueeze(1), bd, stride=stride, padding=pad).transpose(1, 2)
+    return y1.contiguous(), sc.contiguous()
+
+
+def add_layernorm(x, r, gamma, beta, eps=1e-5, out=None):
+    return F.layer_norm(x if r is None else x + r, (x.shape[-1],), gamma, beta, eps)
+
+
+def attention(q, k, v, batch, heads, tq, tk, head_dim):
+    E = heads * head_dim
+    qq = q[:, :E].reshape(batch, tq, heads, head_dim).transpose(1, 2)
+    kk = k[:, :E].reshape(batch, tk, heads, head_dim).transpose(1, 2)
+    vv = v[:, :E].reshape(batch, tk, heads, head_dim).transpose(1, 2)
+    att = torch.softmax(qq @ kk.transpose(-1, -2) / head_dim ** 0.5, -1)
+    return (att @ vv).transpose(1, 2).reshape(batch * tq, E)
+
+
+def add_rows(x, pe, spk, first, second, batch, rows, ch):
+    v = torch.zeros(batch, rows, ch) if x is None else x.reshape(batch, rows, ch)
+    for code in (first, second):
+        if code == ROW_PE:
+            v = v + pe[None, :rows]
+        elif code == ROW_SPK:
+            v = v + spk[:, None]
+    return v.contiguous()
+
+
+def add2(a, b):
+    return a + b
+
+
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre):
+    wm, wk = motion[:, start:start + win_len].clone(), mask[:, start:start + win_len].clone()
+    if pre:
+        wm[:, :pre] = torch.where(wk[:, :pre] == 0, motion[:, start:start + pre], seed)
+        wk[:, :pre] = 0
+    return torch.where(wk == 1, mask_embedding.view(1, 1, -1).expand_as(wm), wm)
+
+
+def l2_argmin(z, codebook, e2):
+    flat = z.reshape(-1, codebook.shape[1])
+    d = (flat ** 2).sum(1, keepdim=True) + e2 - 2 * flat @ codebook.t()
+    return d.argmin(1).reshape(z.shape[:-1])
+
+
+def row_argmax(x):
+    return x.argmax(-1)
+
+
+def gather_rows(codebook, index):
+    return codebook[index]
+
+
+def row_sqnorm(x):
+    return (x ** 2).sum(1)
+
+
+def pose_compose(face, upper, hands, lower, bs, t, device):
+    from oracle import emage_oracle as O
+    z = lambda n: torch.zeros(bs, t, n)
+    aa6 = lambda x: O.rot6d_to_axis_angle(x.reshape(bs, t, -1, 6)).reshape(bs, t, -1)
+    jaw = O.rot6d_to_axis_angle(face[:, :, :6]) if face is not None else z(3)
+    expr = face[:, :, 6:] if face is not None else z(100)
+    up = aa6(upper) if upper is not None else z(39)
+    ha = aa6(hands) if hands is not None else z(90)
+    lo = aa6(lower[:, :, :54]) if lower is not None else z(27)
+    tf = lower[:, :, 54:] if lower is not None else z(7)
+    aa = (O._scatter_joints(up, O.UPPER_JOINTS, bs, t) + O._scatter_joints(ha, O.HANDS_JOINTS, bs, t)
+          + O._scatter_joints(lo, O.LOWER_JOINTS, bs, t))
+    aa[:, :, 66:69] = jaw
+    m4 = torch.cat([O.axis_angle_to_rot6d(aa.reshape(bs, t, 55, 3)).reshape(bs, t, 330), tf], 2)
+    return expr.contiguous(), aa, m4
+
+
+def global_trans(rec, ref_trans, dt, vel_off=54):
+    v = rec[:, :, vel_off:vel_off + 3]
+    x, z = [ref_trans[:, 0:1]], [ref_trans[:, 2:3]]
+    for i in range(1, rec.shape[1]):
+        x.append(v[:, i - 1, 0:1] * dt + x[-1])
+        z.append(v[:, i - 1, 2:3] * dt + z[-1])
+    return torch.stack([torch.cat(x, 1), v[:, :, 1], torch.cat(z, 1)], -1)

@@ -1,0 +1,99 @@
+"""Drop-in boundary checks that need no GPU: checkpoint layout, export list, C-ABI symbols,
+loud failure without CUDA."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from oracle.weights import EMAGE_CFG, VQ_CFGS, load_manifest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _models():
+    from pantomatrix_b200.emage_audio import (EmageAudioConfig, EmageAudioModel, EmageVAEConv, EmageVAEConvConfig,
+                                              EmageVQVAEConv, EmageVQVAEConvConfig)
+    out = {"emage": EmageAudioModel(EmageAudioConfig(**EMAGE_CFG))}
+    for p in ("face", "upper", "hands", "lower"):
+        out["vq_" + p] = EmageVQVAEConv(EmageVQVAEConvConfig(**VQ_CFGS[p]))
+    out["vq_global"] = EmageVAEConv(EmageVAEConvConfig(**VQ_CFGS["global"]))
+    return out
+
+
+def test_state_dict_layout_matches_reference():
+    """Keys, shapes and dtypes equal the reference checkpoints (manifest recorded from the live reference
+    modules), so reference checkpoints load with strict=True."""
+    man = load_manifest()
+    for tag, module in _models().items():
+        sd = module.state_dict()
+        want = {k: tuple(s) for k, s in man[tag]}
+        assert set(sd) == set(want), (tag, sorted(set(sd) ^ set(want))[:10])
+        for k, v in sd.items():
+            assert tuple(v.shape) == want[k], (tag, k, v.shape, want[k])
+            assert v.dtype == (torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+
+
+def test_positional_table_is_bit_identical_to_oracle():
+    from oracle.emage_oracle import pos_table
+    from pantomatrix_b200.emage_audio.pe import periodic_table
+    assert torch.equal(periodic_table(768, 64), pos_table(768, 64))
+
+
+def test_export_list_and_shim():
+    import models.emage_audio as shim
+    import pantomatrix_b200.emage_audio as pkg
+    names = ["EmageAudioConfig", "EmageAudioModel", "EmageVQVAEConvConfig", "EmageVQVAEConv", "EmageVQModel",
+             "EmageVAEConvConfig", "EmageVAEConv"]
+    assert sorted(pkg.__all__) == sorted(names)
+    for n in names:
+        assert getattr(shim, n) is getattr(pkg, n)
+
+
+def test_save_and_from_pretrained_round_trip(tmp_path):
+    from pantomatrix_b200.emage_audio import EmageVQVAEConv, EmageVQVAEConvConfig
+    from oracle.weights import load_synthetic
+    m = load_synthetic(EmageVQVAEConv(EmageVQVAEConvConfig(**VQ_CFGS["face"])), 3, "vq_face")
+    m.save_pretrained(tmp_path / "emage_vq" / "face")
+    assert sorted(os.listdir(tmp_path / "emage_vq" / "face")) == ["config.json", "model.safetensors"]
+    m2 = EmageVQVAEConv.from_pretrained(str(tmp_path), subfolder="emage_vq/face")     # T.py:82 call form
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert m2.quantizer.e_dim == 256 and m2.quantizer.embedding.weight.shape == (256, 256)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/pm_emage.h is exported by the built library and bound in
+    pantomatrix_b200._lib (no compute call is made: there is no GPU here)."""
+    from pantomatrix_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "pm_emage.h")).read()
+    declared = set(re.findall(r"^int\s+(pm_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in pm_emage.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().pm_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly off-GPU instead of computing on the CPU."""
+    from pantomatrix_b200 import _lib
+    m = _models()
+    vq = m["vq_face"]
+    with pytest.raises(_lib.PmError):
+        vq.decode(torch.zeros(1, 8, dtype=torch.long))
+    with pytest.raises(_lib.PmError):
+        m["emage"].forward(torch.zeros(1, 34112), torch.zeros(1, 1, dtype=torch.long),
+                           torch.zeros(1, 64, 337), torch.ones(1, 64, 337))
+
+
+def test_product_never_imports_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "pantomatrix_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(base, f)

@@ -1,0 +1,163 @@
+"""End-to-end parity of the CUDA path (GPU): the drop-in modules against (1) the committed golden outputs
+of the unmodified reference and (2) the live CPU oracle on the same seeded weights and audio.
+
+Gates: emitted VQ code indices bit-exact; SMPL-X parameters within 1e-3 max-abs
+(and geodesic error reported, because axis-angle is discontinuous at pi)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emage_oracle as O
+from oracle.weights import make_checkpoint, synth_audio
+from helpers import build_product, geodesic_deg
+
+pytestmark = pytest.mark.gpu
+PARTS = ("face", "upper", "hands", "lower")
+GOLDEN = ["tail11", "clip10s", "drop_tail", "short40", "seeded"]
+
+
+@pytest.fixture(scope="module")
+def product():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return build_product(seed=0)
+
+
+@pytest.fixture(scope="module")
+def ckpt():
+    return make_checkpoint(seed=0)
+
+
+def _pose_checks(pred, want_aa, want_expr, want_trans, tag):
+    aa = pred["motion_axis_angle"].cpu()
+    geo = geodesic_deg(aa.reshape(*aa.shape[:2], 55, 3), want_aa.reshape(*aa.shape[:2], 55, 3))
+    assert geo.max() < 0.05, (tag, "geodesic deg", geo.max().item())
+    far = (want_aa.reshape(*aa.shape[:2], 55, 3).norm(dim=-1) < 3.0).repeat_interleave(3, dim=-1)
+    assert (aa - want_aa)[far].abs().max() < 1e-3, (tag, (aa - want_aa)[far].abs().max().item())
+    assert (pred["expression"].cpu() - want_expr).abs().max() < 1e-3, tag
+    assert (pred["trans"].cpu() - want_trans).abs().max() < 1e-3, tag
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_matches_reference_golden(case, product, golden_dir):
+    from pantomatrix_b200.pipeline import generate
+    model, vqm = product
+    g = np.load(os.path.join(golden_dir, f"case_{case}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"]))).cuda()
+    mm = torch.from_numpy(g["masked_motion"]).cuda() if "masked_motion" in g else None
+    mk = torch.from_numpy(g["mask"]).cuda() if "mask" in g else None
+    lat, pred = generate(model, vqm, audio, masked_motion=mm, mask=mk)
+    for p in PARTS:
+        assert lat["cls_" + p].shape[1] == g["idx_cls_" + p].shape[1], "emitted length (tail-drop rule)"
+        got = lat["cls_" + p].argmax(-1).cpu().numpy()
+        assert np.array_equal(got, g["idx_cls_" + p]), (case, p, int((got != g["idx_cls_" + p]).sum()))
+        np.testing.assert_allclose(lat["rec_" + p].cpu().numpy()[:, ::7], g["rec_" + p], atol=1e-3, rtol=0)
+        np.testing.assert_allclose(lat["cls_" + p].cpu().numpy()[:, ::7], g["cls_" + p], atol=2e-3, rtol=0)
+    face_idx = vqm.vq_model_face._index_of(lat["rec_face"]).cpu().numpy()
+    assert np.array_equal(face_idx, g["idx_l2_face"])
+    _pose_checks(pred, torch.from_numpy(g["motion_axis_angle"]), torch.from_numpy(g["expression"]),
+                 torch.from_numpy(g["trans"]), case)
+    assert (pred["all_motion4inference"].cpu() - torch.from_numpy(g["all_motion4inference"])).abs().max() < 1e-3
+
+
+def test_single_window_forward_matches_oracle(product, ckpt):
+    """EmageAudioModel.forward (M.py:265-341) on one 64-frame window with a random partial mask."""
+    model, _ = product
+    sd, cfg, vq = ckpt
+    bs = 3
+    g = torch.Generator().manual_seed(7)
+    audio = torch.from_numpy(synth_audio(bs, 34112, 77))
+    motion = torch.randn(bs, 64, 337, generator=g) * 0.3
+    mask = (torch.rand(bs, 64, 337, generator=g) > 0.3).float()
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    with torch.no_grad():
+        want = O.emage_forward(sd, audio, spk, motion, mask)
+    got = model.forward(audio.cuda(), spk.cuda(), motion.cuda(), mask.cuda())
+    for k, v in want.items():
+        assert (got[k].cpu() - v).abs().max() < 1e-3, (k, (got[k].cpu() - v).abs().max().item())
+        if k.startswith("cls_"):
+            assert torch.equal(got[k].argmax(-1).cpu(), v.argmax(-1)), k
+
+
+def test_vq_decode_and_tokenise_match_oracle(product, ckpt):
+    """EmageVQModel.decode (index and latent inputs, zero branches) and map2index (training-side
+    tokenisation, all four L2-argmin lookups)."""
+    _, vqm = product
+    sd, cfg, vq = ckpt
+    bs, t = 2, 37
+    g = torch.Generator().manual_seed(11)
+    idx = {p: torch.randint(0, 256, (bs, t), generator=g) for p in PARTS}
+    lat = {p: torch.randn(bs, t, 256, generator=g) for p in PARTS}
+    with torch.no_grad():
+        want = O.vq_decode(vq, face_latent=lat["face"], upper_index=idx["upper"], hands_index=idx["hands"],
+                           lower_index=idx["lower"], get_global_motion=True, ref_trans=torch.zeros(1, 3))
+        want_partial = O.vq_decode(vq, upper_latent=lat["upper"])
+    got = vqm.decode(face_latent=lat["face"].cuda(), upper_index=idx["upper"].cuda(), hands_index=idx["hands"].cuda(),
+                     lower_index=idx["lower"].cuda(), get_global_motion=True, ref_trans=torch.zeros(1, 3).cuda())
+    _pose_checks(got, want["motion_axis_angle"], want["expression"], want["trans"], "decode")
+    got_partial = vqm.decode(upper_latent=lat["upper"].cuda())
+    assert got_partial["trans"] is None and got_partial["expression"].abs().max() == 0
+    assert geodesic_deg(got_partial["motion_axis_angle"].cpu().reshape(bs, t, 55, 3),
+                        want_partial["motion_axis_angle"].reshape(bs, t, 55, 3)).max() < 0.05
+    # tokenisation: encoder conv stack + L2-argmin for each part
+    rot6d = O.axis_angle_to_rot6d(torch.randn(bs, t, 55, 3, generator=g) * 0.4).reshape(bs, t, 330)
+    expr = torch.randn(bs, t, 100, generator=g)
+    tok = vqm.map2index(rot6d.cuda(), expr.cuda())
+    r = rot6d.reshape(bs, t, 55, 6)
+    inputs = dict(face=torch.cat([r[:, :, 22], expr], 2), upper=r[:, :, list(O.UPPER_JOINTS)].reshape(bs, t, 78),
+                  hands=r[:, :, 25:55].reshape(bs, t, 180),
+                  lower=torch.cat([r[:, :, list(O.LOWER_JOINTS)].reshape(bs, t, 54), torch.zeros(bs, t, 7)], 2))
+    for p in PARTS:
+        psd, pcfg = vq[p]
+        with torch.no_grad():
+            z = O.vq_encoder(psd, "encoder", inputs[p], pcfg["vae_layer"])
+        assert torch.equal(tok[p].cpu(), O.l2_argmin(z, psd["quantizer.embedding.weight"])), p
+
+
+def test_teacher_forced_windows_and_free_run_vs_oracle(product, ckpt):
+    """bs=4 x 10 s: free-running generate() vs the oracle, plus per-window comparison on the oracle's own
+    window inputs (so one flipped near-tie cannot hide or amplify later differences)."""
+    from pantomatrix_b200.pipeline import generate
+    model, vqm = product
+    sd, cfg, vq = ckpt
+    bs = 4
+    audio = torch.from_numpy(synth_audio(bs, 160000, 4321))
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    trace = []
+    with torch.no_grad():
+        want_lat, want_pred = O.emage_generate(sd, cfg, vq, audio, spk, trace=trace)
+    for w in trace:                                                   # teacher-forced single windows
+        got = model.forward(w["audio"].cuda(), spk.cuda(), w["motion"].cuda(), w["mask"].cuda())
+        for p in PARTS:
+            assert torch.equal(got["cls_" + p].argmax(-1).cpu(), w["idx"][p]), p
+            assert (got["rec_" + p].cpu() - w["out"]["rec_" + p]).abs().max() < 1e-3
+    lat, pred = generate(model, vqm, audio.cuda())
+    for p in PARTS:
+        assert torch.equal(lat["cls_" + p].argmax(-1).cpu(), want_lat["cls_" + p].argmax(-1)), p
+    _pose_checks(pred, want_pred["motion_axis_angle"], want_pred["expression"], want_pred["trans"], "free-run")
+
+
+def test_baseline_config_batch32(product, ckpt):
+    """BASELINE configs[1]: 32 clips x 300 frames.  Index agreement must be total on this seeded input;
+    size-independent properties: emitted length, unit-norm rot6d rows, trans integrates its velocities."""
+    from pantomatrix_b200.pipeline import generate
+    model, vqm = product
+    sd, cfg, vq = ckpt
+    bs = 32
+    audio = torch.from_numpy(synth_audio(bs, 160000, 1234))
+    lat, pred = generate(model, vqm, audio.cuda())
+    assert lat["rec_face"].shape == (bs, 300, 256) and pred["motion_axis_angle"].shape == (bs, 300, 165)
+    m4 = pred["all_motion4inference"][:, :, :330].reshape(bs, 300, 55, 2, 3)
+    assert (m4.norm(dim=-1) - 1).abs().max() < 1e-4 and (m4[..., 0, :] * m4[..., 1, :]).sum(-1).abs().max() < 1e-4
+    with torch.no_grad():
+        want_lat, want_pred = O.emage_generate(sd, cfg, vq, audio, torch.zeros(bs, 1, dtype=torch.long))
+    total = mismatched = 0
+    for p in PARTS:
+        a, b = lat["cls_" + p].argmax(-1).cpu(), want_lat["cls_" + p].argmax(-1)
+        total += a.numel()
+        mismatched += int((a != b).sum())
+    assert mismatched == 0, f"{mismatched}/{total} code indices differ from the oracle"
+    _pose_checks(pred, want_pred["motion_axis_angle"], want_pred["expression"], want_pred["trans"], "bs32")

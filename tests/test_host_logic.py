@@ -1,0 +1,78 @@
+"""Host-logic tests (no GPU): the product's Python scheduling - window plan, audio hoisting, BatchNorm
+folding and weight packing, tail-only seed decode, the reference-facing API - run with every kernel
+wrapper replaced by tests/fake_ops.py, and compared with the oracle and the reference's golden outputs.
+The kernels themselves are tested on the GPU (tests/test_kernels_gpu.py, tests/test_emage_gpu.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emage_oracle as O
+from oracle.weights import make_checkpoint, synth_audio
+import fake_ops
+from helpers import build_product
+
+PARTS = ("face", "upper", "hands", "lower")
+
+
+@pytest.fixture()
+def cpu_product(monkeypatch):
+    import pantomatrix_b200.ops as real
+    from pantomatrix_b200.emage_audio import modeling
+    for name in dir(fake_ops):
+        if not name.startswith("_") and callable(getattr(fake_ops, name)) and hasattr(real, name):
+            monkeypatch.setattr(real, name, getattr(fake_ops, name))
+    monkeypatch.setattr(modeling, "_require_cuda", lambda module, what: torch.device("cpu"))
+    return build_product(seed=0, device="cpu")
+
+
+@pytest.mark.parametrize("case", ["tail11", "drop_tail", "short40", "seeded"])
+def test_schedule_reproduces_reference(case, cpu_product, golden_dir):
+    from pantomatrix_b200.pipeline import generate
+    model, vqm = cpu_product
+    g = np.load(os.path.join(golden_dir, f"case_{case}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"])))
+    mm = torch.from_numpy(g["masked_motion"]) if "masked_motion" in g else None
+    mk = torch.from_numpy(g["mask"]) if "mask" in g else None
+    lat, pred = generate(model, vqm, audio, masked_motion=mm, mask=mk)
+    for p in PARTS:
+        assert np.array_equal(lat["cls_" + p].argmax(-1).numpy(), g["idx_cls_" + p]), p
+        np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=5e-4, rtol=0)
+    for k in ("expression", "motion_axis_angle", "trans", "all_motion4inference"):
+        np.testing.assert_allclose(pred[k].numpy(), g[k], atol=1e-3, rtol=0, err_msg=k)   # the 1e-3 pose gate
+
+
+def test_forward_and_decode_api(cpu_product):
+    model, vqm = cpu_product
+    sd, cfg, vq = make_checkpoint(seed=0)
+    bs = 2
+    g = torch.Generator().manual_seed(3)
+    audio = torch.from_numpy(synth_audio(bs, 34112, 5))
+    motion, mask = torch.randn(bs, 64, 337, generator=g) * 0.3, (torch.rand(bs, 64, 337, generator=g) > 0.3).float()
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    with torch.no_grad():
+        want = O.emage_forward(sd, audio, spk, motion, mask)
+    got = model.forward(audio, spk, motion, mask)
+    assert set(got) == set(want)
+    for k in want:
+        assert (got[k] - want[k]).abs().max() < 5e-4, k
+    idx = torch.randint(0, 256, (bs, 20), generator=g)
+    out = vqm.decode(upper_index=idx, lower_index=idx, get_global_motion=True, ref_trans=torch.zeros(1, 3))
+    with torch.no_grad():
+        ref = O.vq_decode(vq, upper_index=idx, lower_index=idx, get_global_motion=True, ref_trans=torch.zeros(1, 3))
+    assert set(out) == {"expression", "all_motion4inference", "motion_axis_angle", "trans"}
+    for k in out:
+        assert (out[k] - ref[k]).abs().max() < 2e-4, k
+    with pytest.raises(UnboundLocalError):
+        vqm.decode()
+    with pytest.raises(ValueError):                     # fewer audio frames than motion frames (reference: cat fails)
+        model.forward(audio[:, :20000], spk, motion, mask)
+
+
+def test_wav_out_len_matches_reference_geometry():
+    from pantomatrix_b200.emage_audio.engine import wav_out_len, window_plan
+    assert wav_out_len(34112) == 64 and wav_out_len(31980) == 60 and wav_out_len(5863) == 12
+    for L in (4, 40, 64, 68, 69, 124, 131, 300):
+        assert window_plan(L, 64, 4) == O.window_plan(L, 64, 4)

@@ -1,0 +1,243 @@
+"""Per-kernel parity tests (GPU): every C-ABI entry point against a plain torch restatement of the same op
+in float64 (or exact equality for integer / copy semantics).  All calls go through pantomatrix_b200.ops,
+i.e. through libpm_emage.so."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pantomatrix_b200 import _lib, ops as o
+    _lib.load()
+    assert _lib.load().pm_device_cc() >= 100, "sm_100a kernels need a Blackwell device"
+    return o
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def _close(got, want, rtol=2e-5, atol=2e-5):
+    want = want.to(torch.float64)
+    err = (got.double() - want).abs()
+    tol = atol + rtol * want.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.3e} (tol {tol.max().item():.3e})"
+
+
+CONV_CASES = [
+    # batch, rows_in, cin, cout, k, stride, pad, act, residual
+    (3, 700, 64, 64, 15, 1, 7, "leaky", True),       # BasicBlock conv2 + shortcut
+    (3, 745, 64, 64, 15, 6, 0, "leaky", False),      # strided conv1
+    (2, 205, 128, 256, 15, 3, 0, "none", False),     # downsample branch
+    (4, 64, 337, 256, 3, 1, 1, "leaky", False),      # motion encoder stem (ragged cin)
+    (4, 11, 256, 61, 3, 1, 1, "none", True),         # ragged cout / short window + ResBlock skip
+    (5, 16, 61, 61, 3, 1, 1, "none", False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_tapgemm_conv(ops, case):
+    b, rows, cin, cout, k, stride, pad, act, use_res = case
+    x = _rand(b, rows, cin, seed=1)
+    w = _rand(cout, cin, k, seed=2, scale=1 / math.sqrt(cin * k))
+    bias = _rand(cout, seed=3, scale=0.1)
+    want = F.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), stride=stride, padding=pad).transpose(1, 2)
+    res = _rand(*want.shape, seed=4) if use_res else None
+    if use_res:
+        want = want + res.double()
+    if act == "leaky":
+        want = F.leaky_relu(want, 0.2)
+    got = ops.tapgemm(x, w.permute(2, 0, 1).contiguous(), bias, stride=stride, pad=pad,
+                      act=ops.ACT_LEAKY if act == "leaky" else ops.ACT_NONE, slope=0.2, residual=res)
+    assert got.shape == want.shape
+    _close(got, want)
+
+
+@pytest.mark.parametrize("m,k,n,act", [(2048, 768, 2304, "none"), (1920, 768, 1536, "relu"), (2048, 1536, 768, "none"),
+                                       (37, 256, 768, "leaky"), (2048, 512, 768, "none")])
+def test_tapgemm_linear(ops, m, k, n, act):
+    x = _rand(32, m // 32 if m % 32 == 0 else 1, k, seed=5) if m % 32 == 0 else _rand(1, m, k, seed=5)
+    w = _rand(n, k, seed=6, scale=1 / math.sqrt(k))
+    bias = _rand(n, seed=7, scale=0.1)
+    res = _rand(*x.shape[:2], n, seed=8)
+    want = F.linear(x.double(), w.double(), bias.double()) + res.double()
+    want = {"none": want, "relu": F.relu(want), "leaky": F.leaky_relu(want, 0.1)}[act]
+    got = ops.tapgemm(x, w.unsqueeze(0), bias, residual=res, slope=0.1,
+                      act={"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "leaky": ops.ACT_LEAKY}[act])
+    _close(got, want)
+
+
+def test_tapgemm_strided_views(ops):
+    """Column-slice input (packed qkv) and column-slice output, as the attention / concat call sites use."""
+    x = _rand(4, 64, 2304, seed=9)
+    w = _rand(256, 768, seed=10, scale=0.03)
+    out = torch.zeros(4, 64, 512, device="cuda")
+    ops.tapgemm(x[:, :, 768:1536], w.unsqueeze(0), None, out=out[:, :, 256:])
+    _close(out[:, :, 256:], F.linear(x[:, :, 768:1536].double(), w.double()))
+    assert out[:, :, :256].abs().max() == 0
+
+
+def test_wav_stem(ops):
+    bs, n, windows, ws, ns = 3, 9000, 2, 3000, 5863
+    audio = _rand(bs, n, seed=11, scale=0.1)
+    w1, wd = _rand(64, 15, seed=12, scale=0.5), _rand(64, 15, seed=13, scale=0.5)
+    b1, bd = _rand(64, seed=14, scale=0.1), _rand(64, seed=15, scale=0.1)
+    y1, sc = ops.wav_stem(audio, n, ws, bs, windows, ns, w1, b1, wd, bd, stride=5, pad=1600, slope=0.01, offset=100)
+    for w in range(windows):
+        sl = audio[:, 100 + w * ws: 100 + w * ws + ns].double().unsqueeze(1)
+        c1 = F.conv1d(sl, w1.double().unsqueeze(1), b1.double(), stride=5, padding=1600).transpose(1, 2)
+        cd = F.conv1d(sl, wd.double().unsqueeze(1), bd.double(), stride=5, padding=1600).transpose(1, 2)
+        _close(y1[w * bs:(w + 1) * bs], F.leaky_relu(c1, 0.01))          # window-major layout
+        _close(sc[w * bs:(w + 1) * bs], cd)
+
+
+@pytest.mark.parametrize("ch", [256, 768])
+def test_add_layernorm(ops, ch):
+    x, r = _rand(301, ch, seed=16, scale=3.0), _rand(301, ch, seed=17)
+    g, b = _rand(ch, seed=18), _rand(ch, seed=19)
+    _close(ops.add_layernorm(x, r, g, b), F.layer_norm((x + r).double(), (ch,), g.double(), b.double(), 1e-5), 1e-5, 1e-5)
+    _close(ops.add_layernorm(x, None, g, b), F.layer_norm(x.double(), (ch,), g.double(), b.double(), 1e-5), 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("bs,tq,tk", [(5, 64, 64), (3, 60, 60), (2, 11, 12), (2, 1, 1)])
+def test_attention(ops, bs, tq, tk):
+    E, H, hd = 768, 4, 192
+    qkv = _rand(bs * tq, 3 * E, seed=20)
+    kv = _rand(bs * tk, 2 * E, seed=21)
+    got = ops.attention(qkv[:, :E], kv[:, :E], kv[:, E:], bs, H, tq, tk, hd)
+    q = qkv[:, :E].double().view(bs, tq, H, hd).transpose(1, 2)
+    k = kv[:, :E].double().view(bs, tk, H, hd).transpose(1, 2)
+    v = kv[:, E:].double().view(bs, tk, H, hd).transpose(1, 2)
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v).transpose(1, 2).reshape(bs * tq, E)
+    _close(got, want, 1e-5, 1e-5)
+
+
+def test_broadcast_adds_are_exact(ops):
+    bs, t, ch = 3, 60, 768
+    x, pe, spk = _rand(bs, t, ch, seed=22), _rand(128, ch, seed=23), _rand(bs, ch, seed=24)
+    got = ops.add_rows(x, pe, spk, ops.ROW_SPK, ops.ROW_PE, bs, t, ch)
+    assert torch.equal(got, (x + spk[:, None]) + pe[None, :t])
+    got = ops.add_rows(None, pe, spk, ops.ROW_SPK, ops.ROW_PE, bs, t, ch)
+    assert torch.equal(got, (spk[:, None] + pe[None, :t]).expand(bs, t, ch))
+    got = ops.add_rows(x, pe, spk, ops.ROW_PE, ops.ROW_SPK, bs, t, ch)
+    assert torch.equal(got, (x + pe[None, :t]) + spk[:, None])
+    a, b = _rand(7, 13, 5, seed=25), _rand(7, 13, 5, seed=26)
+    assert torch.equal(ops.add2(a, b), a + b)
+
+
+def test_window_input_matches_reference_semantics(ops):
+    bs, L, ch, pre, s, t = 3, 130, 337, 4, 60, 64
+    motion, seed, emb = _rand(bs, L, ch, seed=27), _rand(bs, pre, ch, seed=28), _rand(ch, seed=29)
+    mask = (torch.rand(bs, L, ch, generator=torch.Generator().manual_seed(30)) > 0.5).float().cuda()
+    got = ops.window_input(motion, mask, seed, emb, s, t, pre)
+    wm, wk = motion[:, s:s + t].clone(), mask[:, s:s + t].clone()          # M.py:384-391
+    wm[:, :pre] = torch.where(wk[:, :pre] == 0, motion[:, s:s + pre], seed)
+    wk[:, :pre] = 0
+    want = torch.where(wk == 1, emb.view(1, 1, ch).expand_as(wm), wm)      # M.py:267-268
+    assert torch.equal(got, want)
+
+
+def _fp64_margins(z, cb):
+    d = (z.double() ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1) - 2 * z.double() @ cb.double().t()
+    top = d.topk(2, dim=1, largest=False)
+    return top.indices[:, 0], top.values[:, 1] - top.values[:, 0]
+
+
+@pytest.mark.parametrize("rows", [1, 63, 9600])
+def test_l2_argmin_bit_exact(ops, rows):
+    z, cb = _rand(rows, 256, seed=31), _rand(256, 256, seed=32)
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb))
+    want, margin = _fp64_margins(z, cb)
+    decided = margin > 1e-3          # fp32 evaluation of d (|d| ~ 500) cannot order closer pairs reliably
+    assert decided.float().mean() > 0.99
+    assert torch.equal(got[decided], want[decided])
+    # the undecided rows must still pick one of the two near-tied codes
+    d32 = (z ** 2).sum(1, keepdim=True) + (cb ** 2).sum(1) - 2 * z @ cb.t()
+    assert bool(((d32.gather(1, got[:, None])[:, 0] - d32.min(1).values).abs() < 1e-2).all())
+
+
+def test_l2_argmin_ties_pick_first(ops):
+    cb = _rand(256, 256, seed=33)
+    cb[200] = cb[7]                                   # duplicate code: lower index must win (torch.argmin)
+    z = cb[[7, 200, 9]].clone() + 1e-3
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb))
+    assert got.tolist() == [7, 7, 9]
+
+
+def test_l2_argmin_million_rows_optimality(ops):
+    """BASELINE-scale property check: chosen code is a minimiser (within fp32 noise) for 2^20 rows."""
+    rows = 1 << 20
+    z = torch.randn(rows, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(34))
+    cb = _rand(256, 256, seed=35)
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb))
+    assert int(got.min()) >= 0 and int(got.max()) < 256
+    for lo in range(0, rows, 1 << 18):
+        zz = z[lo:lo + (1 << 18)]
+        d = (zz ** 2).sum(1, keepdim=True) + (cb ** 2).sum(1) - 2 * zz @ cb.t()
+        picked = d.gather(1, got[lo:lo + (1 << 18), None])[:, 0]
+        assert bool((picked - d.min(1).values < 5e-3).all())
+
+
+def test_row_argmax_first_max(ops):
+    x = _rand(9600, 256, seed=36)
+    x[5, 17] = x[5, 200] = 50.0                      # tie -> first index
+    x[6, :] = -3.0                                   # all equal -> 0
+    got = ops.row_argmax(x)
+    assert torch.equal(got, torch.max(F.log_softmax(x, dim=1), dim=1)[1]) or torch.equal(got, x.argmax(1))
+    assert got[5].item() == 17 and got[6].item() == 0
+
+
+def test_gather_rows(ops):
+    cb = _rand(256, 256, seed=37)
+    idx = torch.randint(0, 256, (4, 33), generator=torch.Generator().manual_seed(38)).cuda()
+    assert torch.equal(ops.gather_rows(cb, idx), cb[idx])
+
+
+def test_pose_compose_matches_oracle(ops):
+    from oracle import emage_oracle as O
+    from helpers import geodesic_deg
+    bs, t = 3, 50
+    parts = dict(face=_rand(bs, t, 106, seed=39), upper=_rand(bs, t, 78, seed=40), hands=_rand(bs, t, 180, seed=41),
+                 lower=_rand(bs, t, 61, seed=42))
+    expr, aa, m4 = ops.pose_compose(parts["face"], parts["upper"], parts["hands"], parts["lower"], bs, t, "cuda")
+    c = {k: v.cpu() for k, v in parts.items()}
+    jaw = O.rot6d_to_axis_angle(c["face"][:, :, :6])
+    up = O.rot6d_to_axis_angle(c["upper"].reshape(bs, t, -1, 6)).reshape(bs, t, -1)
+    ha = O.rot6d_to_axis_angle(c["hands"].reshape(bs, t, -1, 6)).reshape(bs, t, -1)
+    lo = O.rot6d_to_axis_angle(c["lower"][:, :, :54].reshape(bs, t, -1, 6)).reshape(bs, t, -1)
+    want = (O._scatter_joints(up, O.UPPER_JOINTS, bs, t) + O._scatter_joints(ha, O.HANDS_JOINTS, bs, t)
+            + O._scatter_joints(lo, O.LOWER_JOINTS, bs, t))
+    want[:, :, 66:69] = jaw
+    assert torch.equal(expr.cpu(), c["face"][:, :, 6:])
+    assert torch.equal(m4.cpu()[:, :, 330:], c["lower"][:, :, 54:])
+    geo = geodesic_deg(aa.cpu().reshape(bs, t, 55, 3), want.reshape(bs, t, 55, 3))
+    assert geo.max() < 0.02, geo.max()
+    far = (want.reshape(bs, t, 55, 3).norm(dim=-1) < 3.0).unsqueeze(-1).expand(bs, t, 55, 3).reshape(bs, t, 165)
+    assert (aa.cpu() - want)[far].abs().max() < 1e-4           # away from the pi discontinuity
+    want6 = O.axis_angle_to_rot6d(want.reshape(bs, t, 55, 3)).reshape(bs, t, 330)
+    assert (m4.cpu()[:, :, :330] - want6).abs().max() < 1e-4
+    # the reference's zero branches (M.py:143-146,174-178): eyes and missing parts are identity rotations
+    expr0, aa0, m40 = ops.pose_compose(None, parts["upper"], None, None, bs, t, "cuda")
+    assert expr0.abs().max() == 0 and aa0[:, :, 66:75].abs().max() == 0
+    assert torch.equal(m40[0, 0, 0:6].cpu(), torch.tensor([1.0, 0, 0, 0, 1, 0]))
+
+
+def test_global_trans_sequential_sum(ops):
+    bs, t = 4, 300
+    rec, ref = _rand(bs, t, 61, seed=43), _rand(bs, 3, seed=44)
+    got = ops.global_trans(rec, ref, 1 / 30).cpu()
+    v = rec.cpu()[:, :, 54:57]
+    x, z = [ref.cpu()[:, 0:1]], [ref.cpu()[:, 2:3]]
+    for i in range(1, t):                                        # P.py:107-115
+        x.append(v[:, i - 1, 0:1] * (1 / 30) + x[-1])
+        z.append(v[:, i - 1, 2:3] * (1 / 30) + z[-1])
+    assert torch.equal(got[:, :, 0], torch.cat(x, 1)) and torch.equal(got[:, :, 2], torch.cat(z, 1))
+    assert torch.equal(got[:, :, 1], v[:, :, 1])
