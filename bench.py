@@ -87,30 +87,46 @@ class ClockSampler:
 
 
 def time_cpu_oracle(sample_clips, repeats, warmup):
+    """Times oracle.emage_generate (the CPU port of the reference path) on `sample_clips` x 10 s clips.
+    The thread count is the best of a quick probe over {all cores, 64, 32, 16, 8}: on many-core hosts the
+    small per-window ops of this model run slower with every core than with a subset, and the baseline
+    should be the CPU at its best.  Returns (frames per run, [seconds per run], threads used)."""
     import torch
     from oracle import emage_oracle as O
     from oracle.weights import make_checkpoint, synth_audio
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd, cfg, vq = make_checkpoint(seed=0)
-    audio = torch.from_numpy(synth_audio(sample_clips, N_SAMPLES, 1234))
-    spk = torch.zeros(sample_clips, 1, dtype=torch.long)
+
+    def run(clips):
+        audio = torch.from_numpy(synth_audio(clips, N_SAMPLES, 1234))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.emage_generate(sd, cfg, vq, audio, torch.zeros(clips, 1, dtype=torch.long))
+        return time.perf_counter() - t0
+
+    best, best_t = cores, None
+    cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
+    if len(cands) > 1:
+        for c in cands:
+            torch.set_num_threads(c)
+            run(1)                                   # warm the thread pool / allocator at this width
+            t = run(2)
+            if best_t is None or t < best_t:
+                best, best_t = c, t
+    torch.set_num_threads(best)
     times = []
-    with torch.no_grad():
-        for i in range(warmup + repeats):
-            t0 = time.perf_counter()
-            O.emage_generate(sd, cfg, vq, audio, spk)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    frames = sample_clips * FRAMES_PER_CLIP
-    return frames, times, torch.get_num_threads()
+    for i in range(warmup + repeats):
+        t = run(sample_clips)
+        if i >= warmup:
+            times.append(t)
+    return sample_clips * FRAMES_PER_CLIP, times, best
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = CLIPS_PER_GPU if (os.cpu_count() or 1) >= 16 else 8       # full batch where the host can take it
+    sample = 8                                     # bounded sample of the 32-clip workload (same clip length)
     frames, times, threads = time_cpu_oracle(sample, args.steps, min(args.warmup, 1))
     total = sum(times)
     value = frames * len(times) / total
@@ -121,7 +137,7 @@ def run_reference(args):
         "config": {"workload": f"EMAGE batch32x300f (configs[1]); each step = {sample}-clip x 300-frame sample of it",
                    "sample_clips": sample, "frames_per_clip": FRAMES_PER_CLIP},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} clips x {FRAMES_PER_CLIP} frames per step, fp32, torch CPU ops, all host threads"},
+                         "sample": f"{sample} clips x {FRAMES_PER_CLIP} frames per step, fp32, torch CPU ops; threads = best of a probe over the host's cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -254,7 +270,7 @@ def run_gpu(args):
         gflop, gms, gl = instrumented_gemm_pass(model, vqm, audio, generate, ops)
         achieved = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         peak = peaks["bf16_sustained"]
-        sample = CLIPS_PER_GPU if (os.cpu_count() or 1) >= 16 else 4
+        sample = 8
         cframes, ctimes, cthreads = time_cpu_oracle(sample, 2, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

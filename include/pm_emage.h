@@ -42,17 +42,20 @@ int pm_tapgemm_f32(const float* A, long long a_bs, int lda, int batch, int rows_
                    float* out, long long o_bs, int ldo, void* stream);
 
 /* ---- tap-GEMM on the tcgen05 tensor cores (split-bf16 operands, fp32 TMEM accumulate) -------------
- * Same contract as pm_tapgemm_f32 with stride == 1.  A and W are given as `nsplit` bf16 planes
- * (x = hi + mid + lo), plane stride a_ps / w_ps elements.  `nsplit` 1 = plain bf16, 2 = bf16x3
- * (hi*hi + hi*lo + lo*hi), 3 = bf16x6 (all products down to 2^-24).  The epilogue can write the fp32
- * result and/or its own bf16 split planes for the next GEMM (out_f32 / out_bf16 nullable).
- * Operands are staged by TMA (cp.async.bulk.tensor) with zero fill for the padding rows; descriptors
- * are built on the host inside this call from the raw pointers.  */
+ * Same contract as pm_tapgemm_f32 with stride == 1 (strided convs are passed as stride-1 problems over the
+ * (rows/s, s*cin) view of the input with zero-padded taps).  A and W are `nsplit` bf16 planes (x = p0+p1+p2),
+ * plane strides a_ps / w_ps elements: nsplit 1 = plain bf16, 2 = bf16x3 (p0*p0 + p0*p1 + p1*p0), 3 = bf16x6
+ * (all products down to 2^-24).  W planes are (taps, w_rows, ldw) with w_rows >= cout a multiple of the N
+ * tile (64 if cout <= 64 else 128), zero rows beyond cout.  lda, ldw, a_bs, a_ps, w_ps must be multiples
+ * of 8 elements (TMA 16-byte rule).  The activation is applied to columns < act_cols only (<=0: all).
+ * The epilogue writes the fp32 result and/or its bf16 split planes (out_f32 / out_bf16 nullable).
+ * Operands are staged by TMA (cp.async.bulk.tensor, zero fill for padding rows, tap shift folded into the
+ * row coordinate); descriptors are built on the host inside this call from the raw pointers. */
 int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, int batch, int rows_in, int cin,
-                  const uint16_t* W, long long w_ps, int taps, int pad, int nsplit,
+                  const uint16_t* W, long long w_ps, int w_rows, int ldw, int taps, int pad, int nsplit,
                   const float* bias, int rows_out, int cout,
                   const float* residual, long long r_bs, int ldr,
-                  int act, float slope,
+                  int act, int act_cols, float slope,
                   float* out_f32, long long o_bs, int ldo,
                   uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
                   void* stream);

@@ -115,6 +115,29 @@ def axis_angle_to_rot6d(aa):
     return m[..., :2, :].reshape(*m.shape[:-2], 6)
 
 
+def rot6d_condition(raw, bs, t):
+    """Conditioning of the Gram-Schmidt step (P.py:49-55) per joint: kappa = 1 / min(|a1|, |b2 before its
+    normalisation|).  A decoder-output perturbation eps moves the emitted rotation by ~ eps * kappa rad, so
+    two fp32 evaluations of the same decoder cannot agree better than that.  raw: {part: decoder output}
+    as returned in vq_decode()["_raw"].  Returns (bs, t, 55); joints without a decoder (eyes) get 1."""
+    d6 = torch.zeros(bs, t, 55, 6, dtype=torch.float64)
+    d6[..., 0] = 1.0
+    d6[..., 4] = 1.0
+    if "upper" in raw:
+        d6[:, :, list(UPPER_JOINTS)] = raw["upper"].double().reshape(bs, t, 13, 6)
+    if "hands" in raw:
+        d6[:, :, list(HANDS_JOINTS)] = raw["hands"].double().reshape(bs, t, 30, 6)
+    if "lower" in raw:
+        d6[:, :, list(LOWER_JOINTS)] = raw["lower"].double()[:, :, :54].reshape(bs, t, 9, 6)
+    if "face" in raw:
+        d6[:, :, JAW_JOINT] = raw["face"].double()[:, :, :6]
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    n1 = a1.norm(dim=-1)
+    b1 = a1 / n1.clamp(min=1e-30).unsqueeze(-1)
+    b2 = a2 - (b1 * a2).sum(-1, keepdim=True) * b1
+    return 1.0 / torch.minimum(n1, b2.norm(dim=-1)).clamp(min=1e-30)
+
+
 # SMPL-X joint bookkeeping (M.py:75-90,181): which of the 55 joints each body part owns.
 UPPER_JOINTS = (3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21)
 LOWER_JOINTS = (0, 1, 2, 4, 5, 7, 8, 10, 11)
@@ -337,24 +360,28 @@ def vq_decode(vq, face_index=None, upper_index=None, hands_index=None, lower_ind
             bs, t = ten.shape[:2]
             dt = vq["face"][0]["quantizer.embedding.weight"].dtype
             break
-    used = {}
+    used, raw = {}, {}
     if face_index is not None or face_latent is not None:
         mix, used["face"] = vq_part_decode(vq, "face", face_index, face_latent)
+        raw["face"] = mix
         jaw, expression = rot6d_to_axis_angle(mix[:, :, :6]), mix[:, :, 6:]
     else:
         jaw, expression = torch.zeros(bs, t, 3, dtype=dt), torch.zeros(bs, t, 100, dtype=dt)
     if upper_index is not None or upper_latent is not None:
         u6, used["upper"] = vq_part_decode(vq, "upper", upper_index, upper_latent)
+        raw["upper"] = u6
         upper = rot6d_to_axis_angle(u6.reshape(bs, t, -1, 6)).reshape(bs, t, -1)
     else:
         upper = torch.zeros(bs, t, 39, dtype=dt)
     if hands_index is not None or hands_latent is not None:
         h6, used["hands"] = vq_part_decode(vq, "hands", hands_index, hands_latent)
+        raw["hands"] = h6
         hands = rot6d_to_axis_angle(h6.reshape(bs, t, -1, 6)).reshape(bs, t, -1)
     else:
         hands = torch.zeros(bs, t, 90, dtype=dt)
     if lower_index is not None or lower_latent is not None:
         lower_mix, used["lower"] = vq_part_decode(vq, "lower", lower_index, lower_latent)
+        raw["lower"] = lower_mix
         l6, transfoot = lower_mix[:, :, :-7], lower_mix[:, :, -7:]
         lower = rot6d_to_axis_angle(l6.reshape(bs, t, -1, 6)).reshape(bs, t, -1)
     else:                                                                               # M.py:174-178
@@ -367,7 +394,7 @@ def vq_decode(vq, face_index=None, upper_index=None, hands_index=None, lower_ind
     aa[:, :, 3 * JAW_JOINT:3 * JAW_JOINT + 3] = jaw                                     # M.py:185
     rot6d = axis_angle_to_rot6d(aa.reshape(bs, t, 55, 3)).reshape(bs, t, 330)
     out = dict(expression=expression, all_motion4inference=torch.cat([rot6d, transfoot], 2),
-               motion_axis_angle=aa, trans=None, _index=used)
+               motion_axis_angle=aa, trans=None, _index=used, _raw=raw)
     if get_global_motion:
         out["trans"] = global_motion(vq, lower_mix, ref_trans)
     return out

@@ -1,14 +1,433 @@
-// tcgen05 tap-GEMM (placeholder until the kernel lands): exported so the ABI is complete.
+// tcgen05 tap-GEMM: Conv1d (stride 1, any taps / zero padding) and Linear on the Blackwell tensor cores.
+//
+//   out[b,l,n] = act( bias[n] + sum_t sum_c A[b, l+t-pad, c] * W[t,n,c] + residual[b,l,n] )
+//
+// Operands are split-bf16 planes (x ~ p0 + p1 + p2, each plane bf16): nsplit 1 = plain bf16, 2 = bf16x3
+// (p0*p0 + p0*p1 + p1*p0), 3 = bf16x6 (every product down to 2^-24): all products accumulate in one fp32
+// TMEM accumulator, so the result has fp32-grade accuracy at tensor-core rates.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   TMA producer  - cp.async.bulk.tensor: A box (64 ch x R rows x NB clips) per plane, with the tap
+//                            shift folded into the row coordinate (im2col-free; padding rows are TMA zero fill),
+//                            W box (64 ch x BN rows) per plane; 128B-swizzled K-major smem tiles; mbarrier ring
+//   warp 1   MMA issuer    - one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//                            tcgen05.commit releases smem stages / publishes the accumulator; owns TMEM alloc
+//   warps 2-5 epilogue     - tcgen05.ld (32 lanes x 32 columns) -> bias / residual / activation -> fp32 store
+//                            and/or bf16 split planes for the next GEMM
+// Contract and reference call sites: include/pm_emage.h (pm_tapgemm_tc).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
 
-extern "C" int pm_tapgemm_tc(const uint16_t*, long long, long long, int, int, int, int, const uint16_t*, long long,
-                             int, int, int, const float*, int, int, const float*, long long, int, int, float,
-                             float*, long long, int, uint16_t*, long long, long long, int, int, void*) {
-  return PM_EUNSUPPORTED;
+namespace {
+
+constexpr int BM = 128;             // tile rows (UMMA M)
+constexpr int BK = 64;              // bf16 channels per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KB per plane
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct TcParams {
+  int taps, pad, nsplit, kblocks;   // kblocks = ceil(cin / 64)
+  int rows_out, cout, batch;
+  int R, NB;                        // tile = NB clips x R rows (R * NB == 128)
+  int w_rows;                       // rows per tap in the packed weight tensor (>= cout, multiple of BN)
+  const float* bias;
+  const float* residual; long long r_bs; int ldr;
+  int act, act_cols; float slope;
+  float* out_f32; long long o_bs; int ldo;
+  __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
+  int stages;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-extern "C" int pm_split_bf16(const float*, long long, int, int, int, int, uint16_t*, long long, long long, int, int,
-                             void*) {
-  return PM_EUNSUPPORTED;
+__device__ __forceinline__ void split3(float v, int nsplit, __nv_bfloat16 (&p)[3]) {
+  p[0] = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(p[0]);
+  p[1] = __float2bfloat16_rn(r);
+  r -= __bfloat162float(p[1]);
+  p[2] = __float2bfloat16_rn(r);
+  (void)nsplit;
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_w,
+                                                                    const TcParams p) {
+  constexpr int W_TILE_BYTES = BN * BK * 2;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;      // power of two >= 32 (BN is 64, 128 or 256)
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][nsplit A tiles][nsplit W tiles] (1024-aligned), then barriers
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p.nsplit * (A_TILE_BYTES + W_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                       // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
+  uint64_t* acc_bar = bars + 2 * MAX_STAGES;       // accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l0 = blockIdx.x * p.R;
+  const int n0 = blockIdx.y * BN;
+  const int b0 = blockIdx.z * p.NB;
+  const int n_iter = p.taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(acc_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)stage_bytes;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const int tap = it / p.kblocks, kb = it % p.kblocks;
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, tx);
+        uint8_t* st = tiles + (size_t)s * stage_bytes;
+        for (int pl = 0; pl < p.nsplit; ++pl) {
+          tma_load_4d(smem_u32(st + pl * A_TILE_BYTES), &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+          tma_load_3d(smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES), &map_w, bar, kb * BK,
+                      tap * p.w_rows + n0, pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(tiles + (size_t)s * stage_bytes);
+        const uint32_t w_base = a_base + p.nsplit * A_TILE_BYTES;
+        // products ordered small -> large: (i,j) with i + j < nsplit
+        for (int sum = p.nsplit - 1; sum >= 0; --sum) {
+          for (int i = 0; i <= sum; ++i) {
+            const int j = sum - i;
+            const uint32_t a_t = a_base + i * A_TILE_BYTES, w_t = w_base + j * W_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              tc_mma_bf16(tmem_base, umma_desc(a_t + k * UMMA_K * 2), umma_desc(w_t + k * UMMA_K * 2), IDESC, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        tc_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
+      }
+      tc_commit(smem_u32(acc_bar));                      // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                         // tile row == TMEM lane
+    const int b = b0 + r / p.R;
+    const int l = l0 + r % p.R;
+    const bool row_ok = b < p.batch && l < p.rows_out;
+    mbar_wait(smem_u32(acc_bar), 0);
+    tc_fence_after();
+    float* of = p.out_f32 ? p.out_f32 + (long long)b * p.o_bs + (long long)l * p.ldo : nullptr;
+    const float* rs = p.residual ? p.residual + (long long)b * p.r_bs + (long long)l * p.ldr : nullptr;
+    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)b * p.ob_bs + (long long)l * p.ldob : nullptr;
+    const bool vec_f = of && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
+    const bool vec_r = rs && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
+    const bool vec_b = ob && ((p.ldob & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0) &&
+                       ((p.ob_bs & 7) == 0) && ((p.ob_ps & 7) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t acc[32];
+      __syncwarp();                                                                // .sync.aligned: whole warp converged
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
+      const int n = n0 + c0;
+      if (row_ok && n < p.cout) {
+      float v[32];
+      const bool full = n + 32 <= p.cout;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (full || n + j < p.cout) v[j] += __ldg(p.bias + n + j);
+      }
+      if (rs) {
+        if (vec_r && full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(rs + n + 4 * j);
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n + j < p.cout) v[j] += rs[n + j];
+        }
+      }
+      if (p.act != PM_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n + j < p.act_cols) v[j] = pm_act(v[j], p.act, p.slope);
+      }
+      if (of) {
+        if (vec_f && full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(of + n + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n + j < p.cout) of[n + j] = v[j];
+        }
+      }
+      if (ob) {
+        for (int pl = 0; pl < p.out_nsplit; ++pl) {
+          __nv_bfloat16* dst = ob + (long long)pl * p.ob_ps + n;
+          __align__(16) __nv_bfloat16 h[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            __nv_bfloat16 pp[3];
+            split3(v[j], p.out_nsplit, pp);
+            h[j] = pp[pl];
+          }
+          if (vec_b && full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(h)[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n + j < p.cout) dst[j] = h[j];
+          }
+        }
+      }
+      }  // row_ok
+    }
+  }
+
+  // teardown: everyone done with TMEM before the owning warp frees it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long x_bs, int ldx, int rows,
+                                                         int ch, __nv_bfloat16* __restrict__ out, long long o_ps,
+                                                         long long o_bs, int ldo, int nsplit, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ch);
+    const long long br = i / ch;
+    const int r = (int)(br % rows);
+    const long long b = br / rows;
+    const float v = x[b * x_bs + (long long)r * ldx + c];
+    __nv_bfloat16 pp[3];
+    split3(v, nsplit, pp);
+    __nv_bfloat16* o = out + b * o_bs + (long long)r * ldo + c;
+    for (int pl = 0; pl < nsplit; ++pl) o[(long long)pl * o_ps] = pp[pl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+            ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
+  const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return PM_EUNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
+  PM_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, int batch, int rows_in, int cin,
+                             const uint16_t* W, long long w_ps, int w_rows, int ldw, int taps, int pad, int nsplit,
+                             const float* bias, int rows_out, int cout,
+                             const float* residual, long long r_bs, int ldr,
+                             int act, int act_cols, float slope,
+                             float* out_f32, long long o_bs, int ldo,
+                             uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
+                             void* stream) {
+  PM_REQUIRE(A && W && (out_f32 || out_bf16));
+  PM_REQUIRE(batch > 0 && rows_in > 0 && rows_out > 0 && cin > 0 && cout > 0 && taps > 0);
+  PM_REQUIRE(nsplit >= 1 && nsplit <= 3 && (!out_bf16 || (out_nsplit >= 1 && out_nsplit <= 3)));
+  PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_LEAKY);
+  // TMA: 16-byte aligned base and strides
+  PM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  PM_REQUIRE((lda & 7) == 0 && (ldw & 7) == 0 && lda >= cin && ldw >= cin && w_rows >= cout);
+  PM_REQUIRE(batch == 1 || (a_bs & 7) == 0);
+  PM_REQUIRE(nsplit == 1 || ((a_ps & 7) == 0 && (w_ps & 7) == 0));
+  PM_REQUIRE(!out_f32 || ldo >= cout);
+  PM_REQUIRE(!out_bf16 || ldob >= cout);
+  PM_REQUIRE(!residual || ldr >= cout);
+
+  const int BNsel = cout <= 64 ? 64 : 128;
+  PM_REQUIRE(w_rows % BNsel == 0);
+
+  int R = 128;
+  if (rows_out <= 64 && batch > 1) { R = 16; while (R < rows_out) R <<= 1; }
+  const int NB = 128 / R;
+
+  TcParams p;
+  p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
+  p.rows_out = rows_out; p.cout = cout; p.batch = batch; p.R = R; p.NB = NB; p.w_rows = w_rows;
+  p.bias = bias; p.residual = residual; p.r_bs = r_bs; p.ldr = ldr;
+  p.act = act; p.act_cols = act_cols <= 0 ? cout : act_cols; p.slope = slope;
+  p.out_f32 = out_f32; p.o_bs = o_bs; p.ldo = ldo;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ob_ps = ob_ps; p.ob_bs = ob_bs; p.ldob = ldob;
+  p.out_nsplit = out_bf16 ? out_nsplit : 0;
+  p.stages = 0;
+
+  CUtensorMap ma, mw;
+  {
+    const long long bs_el = batch > 1 ? a_bs : (long long)rows_in * lda;
+    const long long ps_el = nsplit > 1 ? a_ps : bs_el * batch;
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows_in, (cuuint64_t)batch, (cuuint64_t)nsplit};
+    cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)R, (cuuint32_t)NB, 1};
+    if (!encode_map(&ma, A, 4, dims, strides, box)) return PM_EBADARG;
+  }
+  {
+    const long long ps_el = nsplit > 1 ? w_ps : (long long)taps * w_rows * ldw;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps * w_rows, (cuuint64_t)nsplit};
+    cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ps_el * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
+    if (!encode_map(&mw, W, 3, dims, strides, box)) return PM_EBADARG;
+  }
+  dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
+  PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
+  if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream);
+  return launch<128>(ma, mw, p, grid, (cudaStream_t)stream);
+}
+
+extern "C" int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,
+                             uint16_t* out, long long o_ps, long long o_bs, int ldo, int nsplit, void* stream) {
+  PM_REQUIRE(x && out && batch >= 0 && rows >= 0 && ch > 0 && ldx >= ch && ldo >= ch && nsplit >= 1 && nsplit <= 3);
+  const long long total = (long long)batch * rows * ch;
+  if (total == 0) return PM_OK;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch,
+                                                                  reinterpret_cast<__nv_bfloat16*>(out), o_ps, o_bs, ldo,
+                                                                  nsplit, total);
+  PM_LAUNCH_CHECK();
 }

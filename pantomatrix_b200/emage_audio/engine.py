@@ -46,15 +46,74 @@ def wav_out_len(n: int) -> int:
     return length
 
 
+# Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores
+# with plain bf16 / bf16x3 / bf16x6 split operands (see csrc/pm_tapgemm_tc.cu).
+PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3}
+_STATE = {"nsplit": PRECISIONS["fp32"]}
+
+
+def set_precision(name: str) -> None:
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+    _STATE["nsplit"] = PRECISIONS[name]
+
+
+def get_precision() -> str:
+    return next(k for k, v in PRECISIONS.items() if v == _STATE["nsplit"])
+
+
 class _Conv:
-    __slots__ = ("w", "b", "stride", "pad")
+    """One Conv1d / Linear: fp32 tap-major weights (taps, cout, cin) + lazily packed bf16 planes."""
+    __slots__ = ("w", "b", "stride", "pad", "_packed")
 
     def __init__(self, w, b, stride=1, pad=0):
         self.w, self.b, self.stride, self.pad = w, b, stride, pad
+        self._packed = {}
+
+    def packed(self, nsplit):
+        """bf16 planes for the tensor-core engine.  A stride-s conv is packed as the equivalent stride-1 conv
+        over the (rows/s, s*cin) view of its input: tap k = s*q + r lands in tap q, channel block r; taps
+        beyond the kernel size are zero."""
+        if nsplit not in self._packed:
+            w, s = self.w, self.stride
+            if s > 1:
+                taps, cout, cin = w.shape
+                wp = torch.zeros(-(-taps // s), cout, s * cin, device=w.device, dtype=w.dtype)
+                for k in range(taps):
+                    wp[k // s, :, (k % s) * cin:(k % s + 1) * cin] = w[k]
+                w = wp
+            self._packed[nsplit] = ops.PackedW(w, nsplit)
+        return self._packed[nsplit]
 
     def __call__(self, x, act=ops.ACT_NONE, slope=0.0, residual=None, out=None):
-        return ops.tapgemm(x, self.w, self.b, stride=self.stride, pad=self.pad, act=act, slope=slope,
-                           residual=residual, out=out)
+        ns = _STATE["nsplit"]
+        if ns == 0:
+            return ops.tapgemm(x, self.w, self.b, stride=self.stride, pad=self.pad, act=act, slope=slope,
+                               residual=residual, out=out)
+        batch, rows, cin = x.shape
+        taps, cout, _ = self.w.shape
+        s = self.stride
+        if s == 1:
+            rows_out = rows + 2 * self.pad - taps + 1
+            flat = (taps == 1 and batch > 1 and x.is_contiguous() and (out is None or out.is_contiguous())
+                    and (residual is None or residual.is_contiguous()))
+            if out is None:
+                out = torch.empty(batch, rows_out, cout, device=x.device, dtype=torch.float32)
+            if flat:                                       # a Linear over all clips is one tall matrix
+                ops.tapgemm_tc(ops.split_bf16(x.view(1, batch * rows, cin), ns), self.packed(ns), self.b,
+                               rows_out=batch * rows, act=act, slope=slope, out=out.view(1, batch * rows, cout),
+                               residual=None if residual is None else residual.view(1, batch * rows, cout))
+            else:
+                ops.tapgemm_tc(ops.split_bf16(x, ns), self.packed(ns), self.b, rows_out=rows_out, pad=self.pad,
+                               act=act, slope=slope, residual=residual, out=out)
+            return out
+        assert self.pad == 0 and x.is_contiguous()
+        rows_out = (rows - taps) // s + 1
+        a = ops.split_bf16(x, ns, slack_rows=s)
+        assert a.t.stride(2) == cin, "strided view needs unpadded channel rows"
+        o, _ = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, act=act, slope=slope, residual=residual,
+                              out=out, a_view=(-(-rows // s), s * cin, s * cin))
+        return o
 
 
 class _Linear(_Conv):

@@ -204,3 +204,103 @@ def global_trans(rec, ref_trans, dt, vel_off=54):
     _call("pm_global_trans_f32", rec.data_ptr(), ld, vel_off, ref_trans.data_ptr(), float(dt), trans.data_ptr(),
           bs, t, _stream())
     return trans
+
+
+# ------------------------------------------------------------------------------------------------------
+# tcgen05 tensor-core engine: split-bf16 planes
+# ------------------------------------------------------------------------------------------------------
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Planes:
+    """`nsplit` bf16 planes of a (batch, rows, ch) activation: tensor (nsplit, batch, rows_alloc, ld) bf16
+    with x ~ sum_p planes[p].  Only [:, :, :rows, :ch] is meaningful."""
+    __slots__ = ("t", "rows", "ch")
+
+    def __init__(self, t, rows, ch):
+        self.t, self.rows, self.ch = t, rows, ch
+
+    @property
+    def nsplit(self):
+        return self.t.shape[0]
+
+    @property
+    def batch(self):
+        return self.t.shape[1]
+
+
+def split_bf16(x, nsplit, slack_rows=0):
+    """fp32 (batch, rows, ch) view -> Planes (ld = ch rounded up to 8).  `slack_rows` zeroed rows are
+    appended after the last clip for strided-view consumers."""
+    _chk(x)
+    batch, rows, ch = x.shape
+    ld = _round_up(ch, 8)
+    if slack_rows:
+        buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=x.device, dtype=torch.bfloat16)
+        buf[:, batch * rows:].zero_()
+        t = buf[:, :batch * rows].view(nsplit, batch, rows, ld)
+        ps = buf.stride(0)
+    else:
+        t = torch.empty(nsplit, batch, rows, ld, device=x.device, dtype=torch.bfloat16)
+        ps = t.stride(0)
+    x_bs, ldx = _bs_ld(x)
+    _call("pm_split_bf16", x.data_ptr(), x_bs, ldx, batch, rows, ch, t.data_ptr(), ps, rows * ld, ld, nsplit, _stream())
+    return Planes(t, rows, ch)
+
+
+class PackedW:
+    """Weights of one tap-GEMM for the tensor-core engine: (nsplit, taps, w_rows, ldw) bf16 planes."""
+    __slots__ = ("t", "taps", "cout", "cin", "w_rows", "ldw")
+
+    def __init__(self, w, nsplit):
+        """w: fp32 (taps, cout, cin)."""
+        taps, cout, cin = w.shape
+        bn = 64 if cout <= 64 else 128
+        self.taps, self.cout, self.cin = taps, cout, cin
+        self.w_rows, self.ldw = _round_up(cout, bn), _round_up(cin, 8)
+        full = torch.zeros(taps, self.w_rows, self.ldw, device=w.device, dtype=torch.float32)
+        full[:, :cout, :cin] = w
+        planes, rem = [], full
+        for _ in range(nsplit):                       # round-to-nearest-even, same as the device split
+            p = rem.to(torch.bfloat16)
+            planes.append(p)
+            rem = rem - p.float()
+        self.t = torch.stack(planes).contiguous()
+
+
+def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0,
+               residual=None, want_f32=True, out_nsplit=0, out=None, a_view=None):
+    """Tensor-core tap-GEMM.  `a_view` = (rows_in, cin, lda) overrides the logical view of the A planes
+    (strided convs pass the (rows/s, s*C) view of the same memory).  Returns (fp32 out | None, Planes | None)."""
+    t = a.t
+    nsplit, batch = t.shape[0], t.shape[1]
+    assert nsplit == w.t.shape[0], "A and W must use the same split"
+    rows_a, cin, lda = (a.rows, a.ch, t.stride(2)) if a_view is None else a_view
+    if rows_in is not None:
+        rows_a = rows_in
+    assert cin == w.cin, (cin, w.cin)
+    cout = w.cout
+    dev = t.device
+    out_f = None
+    if want_f32:
+        out_f = out if out is not None else torch.empty(batch, rows_out, cout, device=dev, dtype=torch.float32)
+        assert out_f.shape == (batch, rows_out, cout)
+    o_bs, ldo = _bs_ld(out_f) if out_f is not None else (0, 0)
+    out_p = None
+    if out_nsplit:
+        ldob = _round_up(cout, 8)
+        out_p = Planes(torch.empty(out_nsplit, batch, rows_out, ldob, device=dev, dtype=torch.bfloat16), rows_out, cout)
+    r_bs, ldr = _bs_ld(residual) if residual is not None else (0, 0)
+    if residual is not None:
+        _chk(residual)
+        assert residual.shape == (batch, rows_out, cout)
+    _call("pm_tapgemm_tc", t.data_ptr(), t.stride(0), t.stride(1), lda, batch, rows_a, cin,
+          w.t.data_ptr(), w.t.stride(0), w.w_rows, w.ldw, w.taps, pad, nsplit,
+          _ptr(bias), rows_out, cout, _ptr(residual), r_bs, ldr, act, act_cols, float(slope),
+          _ptr(out_f), o_bs, ldo,
+          None if out_p is None else out_p.t.data_ptr(), 0 if out_p is None else out_p.t.stride(0),
+          0 if out_p is None else out_p.t.stride(1), 0 if out_p is None else out_p.t.stride(2), out_nsplit, _stream())
+    return out_f, out_p

@@ -116,3 +116,65 @@ def global_trans(rec, ref_trans, dt, vel_off=54):
         x.append(v[:, i - 1, 0:1] * dt + x[-1])
         z.append(v[:, i - 1, 2:3] * dt + z[-1])
     return torch.stack([torch.cat(x, 1), v[:, :, 1], torch.cat(z, 1)], -1)
+
+
+# ---- tensor-core engine stand-ins (same Planes / PackedW containers as the product) --------------------
+from pantomatrix_b200.ops import PackedW, Planes, _round_up  # noqa: E402,F401
+
+
+def _split(v, nsplit):
+    planes, rem = [], v
+    for _ in range(nsplit):
+        p = rem.to(torch.bfloat16)
+        planes.append(p)
+        rem = rem - p.float()
+    return planes
+
+
+def split_bf16(x, nsplit, slack_rows=0):
+    batch, rows, ch = x.shape
+    ld = _round_up(ch, 8)
+    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=torch.bfloat16)
+    buf[:, batch * rows:] = 0
+    for i, p in enumerate(_split(x.reshape(batch * rows, ch).float(), nsplit)):
+        buf[i, :batch * rows, :ch] = p
+    return Planes(buf[:, :batch * rows].view(nsplit, batch, rows, ld), rows, ch)
+
+
+def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0, residual=None,
+               want_f32=True, out_nsplit=0, out=None, a_view=None):
+    t = a.t
+    nsplit, batch = t.shape[0], t.shape[1]
+    rows_a, cin, lda = (a.rows, a.ch, t.stride(2)) if a_view is None else a_view
+    # the logical (batch, rows_a, cin) view of the plane memory, exactly as the TMA descriptor addresses it
+    x = sum(torch.as_strided(t[i], (batch, rows_a, cin), (t.stride(1), lda, 1)).float() for i in range(nsplit))
+    wf = w.t[:, :, :w.cout, :w.cin].float().sum(0)                       # (taps, cout, cin)
+    # products the kernel forms: all (i, j) with i + j < nsplit
+    y = 0
+    for i in range(nsplit):
+        xi = torch.as_strided(t[i], (batch, rows_a, cin), (t.stride(1), lda, 1)).float()
+        for j in range(nsplit - i):
+            wj = w.t[j, :, :w.cout, :w.cin].float()
+            y = y + F.conv1d(xi.transpose(1, 2), wj.permute(1, 2, 0), None, padding=pad).transpose(1, 2)
+    y = y[:, :rows_out]
+    if bias is not None:
+        y = y + bias
+    if residual is not None:
+        y = y + residual
+    if act != ACT_NONE:
+        cols = w.cout if act_cols <= 0 else act_cols
+        y = torch.cat([_act(y[..., :cols], act, slope), y[..., cols:]], -1)
+    assert torch.isfinite(y).all(), "read uninitialised plane memory"
+    out_p = None
+    if out_nsplit:
+        ld = _round_up(w.cout, 8)
+        tt = torch.zeros(out_nsplit, batch, rows_out, ld, dtype=torch.bfloat16)
+        for i, p in enumerate(_split(y, out_nsplit)):
+            tt[i, :, :, :w.cout] = p
+        out_p = Planes(tt, rows_out, w.cout)
+    if want_f32:
+        if out is not None:
+            out.copy_(y)
+            y = out
+        return y.contiguous() if out is None else y, out_p
+    return None, out_p

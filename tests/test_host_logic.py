@@ -76,3 +76,23 @@ def test_wav_out_len_matches_reference_geometry():
     assert wav_out_len(34112) == 64 and wav_out_len(31980) == 60 and wav_out_len(5863) == 12
     for L in (4, 40, 64, 68, 69, 124, 131, 300):
         assert window_plan(L, 64, 4) == O.window_plan(L, 64, 4)
+
+
+@pytest.mark.parametrize("precision,atol", [("bf16x6", 5e-4), ("bf16x3", 5e-3)])
+def test_tensor_core_schedule_host_logic(cpu_product, golden_dir, precision, atol):
+    """The tensor-core engine's host side (weight packing into padded bf16 planes, strided convs as reshaped
+    stride-1 problems, clips-per-tile views) reproduces the reference with the kernels emulated."""
+    from pantomatrix_b200.emage_audio import engine
+    from pantomatrix_b200.pipeline import generate
+    model, vqm = cpu_product
+    g = np.load(os.path.join(golden_dir, "case_tail11.npz"))
+    audio = torch.from_numpy(synth_audio(int(g["bs"]), int(g["n_samples"]), int(g["audio_seed"])))
+    engine.set_precision(precision)
+    try:
+        lat, pred = generate(model, vqm, audio)
+    finally:
+        engine.set_precision("fp32")
+    for p in PARTS:
+        np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=atol, rtol=0)
+        agree = (lat["cls_" + p].argmax(-1).numpy() == g["idx_cls_" + p]).mean()
+        assert agree > (0.999 if precision == "bf16x6" else 0.97), (p, agree)
