@@ -33,6 +33,10 @@ CLIPS_PER_GPU = 32
 N_SAMPLES = 160000                    # 10 s @ 16 kHz -> 300 frames
 FRAMES_PER_CLIP = 300
 FLOP_PER_FRAME = 364.7e6              # algorithmic work per emitted frame
+DTYPES = {"fp32": "f32", "bf16x6": "bf16x6 (split-bf16 operands, f32 accumulate)",
+          "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)", "bf16": "bf16"}
+ENGINES = {"fp32": "fp32 SIMT tap-GEMM", "bf16x6": "tcgen05 tap-GEMM, 6 bf16 products per fp32 product",
+           "bf16x3": "tcgen05 tap-GEMM, 3 bf16 products per fp32 product", "bf16": "tcgen05 tap-GEMM, plain bf16"}
 METRIC = "motion_frames_per_sec"
 UNIT = "frames/s"
 
@@ -164,8 +168,10 @@ def instrumented_gemm_pass(model, vqm, audio, generate, ops):
             e.record()
             if name == "pm_tapgemm_f32":      # (A,a_bs,lda,batch,rows_in,cin,W,bias,taps,stride,pad,rows_out,cout,...)
                 batch, cin, taps, rows_out, cout = a[3], a[5], a[8], a[11], a[12]
-            else:                              # (A,a_ps,a_bs,lda,batch,rows_in,cin,W,w_ps,taps,pad,nsplit,bias,rows_out,cout,..)
-                batch, cin, taps, rows_out, cout = a[4], a[6], a[9], a[13], a[14]
+            else:      # (A,a_ps,a_bs,lda,batch,rows_in,cin,W,w_ps,w_rows,ldw,taps,pad,nsplit,bias,rows_out,cout,..)
+                batch, cin, taps, rows_out, cout = a[4], a[6], a[11], a[15], a[16]
+                if taps * cin in (18 * 64, 18 * 128):      # k=15 stride-6/3 convs run as 3x(6C) / 5x(3C) taps:
+                    taps, cin = 15, cin * taps // 18       # count the algorithmic 15 taps, not the zero padding
             records.append((2.0 * batch * rows_out * cout * cin * taps, s, e))
         else:
             real(name, *a)
@@ -187,7 +193,9 @@ def run_gpu(args):
     from helpers import build_product
     from oracle.weights import synth_audio
     from pantomatrix_b200 import ops
-    from pantomatrix_b200.pipeline import generate
+    from pantomatrix_b200.emage_audio import engine
+    from pantomatrix_b200.pipeline import CapturedPipeline, generate
+    engine.set_precision(args.precision)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,8 +225,24 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
+    cap = CapturedPipeline(model, vqm, clips, N_SAMPLES) if args.graph else None
+    if cap is not None:
+        cap.audio.copy_(audio)
+
+    def step_resident():
+        if cap is not None:
+            cap.graph.replay()
+            ops.launch_count += cap.kernels_per_replay
+        else:
+            generate(model, vqm, audio)
+
+    def step_e2e():
+        if cap is not None:
+            return cap(host_audio)[1]
+        return generate(model, vqm, host_audio.to(dev, non_blocking=True))[1]
+
     for _ in range(max(args.warmup, 3)):
-        generate(model, vqm, audio)
+        step_resident()
     sync_all()
 
     sampler = ClockSampler(local)
@@ -232,7 +256,7 @@ def run_gpu(args):
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                   # evict L2 between timed iterations (outside the bracket)
         starts[i].record()
-        generate(model, vqm, audio)
+        step_resident()
         ends[i].record()
     sync_all()
     launches = ops.launch_count - launches0
@@ -249,8 +273,7 @@ def run_gpu(args):
         flush.fill_(i & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        a = host_audio.to(dev, non_blocking=True)
-        _, pred = generate(model, vqm, a)
+        pred = step_e2e()
         for k, v in out_host.items():
             v.copy_(pred[k], non_blocking=True)
         torch.cuda.synchronize()
@@ -275,11 +298,11 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPES[args.precision], "data": "synthetic",
             "config": {"workload": "EMAGE batch32x300f per GPU (BASELINE configs[1]; configs[4] at 8 GPUs)",
                        "clips_per_gpu": clips, "frames_per_clip": FRAMES_PER_CLIP, "audio_samples": N_SAMPLES,
                        "weights": "synthetic seeded checkpoint (oracle/weights.py), reference key layout",
-                       "engine": "fp32 SIMT tap-GEMM", "l2": "256 MB flush between timed steps; weights 0.56 GB > L2",
+                       "engine": ENGINES[args.precision], "cuda_graph": bool(args.graph), "l2": "256 MB flush between timed steps; weights 0.56 GB > L2",
                        "parallelism": f"dp{world} (clip sharding, NCCL weight broadcast at load only)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock incl. H2D/D2H, pinned host buffers"},
@@ -305,6 +328,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PM_EMAGE_PRECISION", "fp32"), choices=list(DTYPES))
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as one CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

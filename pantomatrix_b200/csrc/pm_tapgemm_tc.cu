@@ -123,7 +123,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
                                                                     const TcParams p) {
   constexpr int W_TILE_BYTES = BN * BK * 2;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;      // power of two >= 32 (BN is 64, 128 or 256)
+  // Three fp32 accumulators in TMEM: two "main" ones that take the p0*p0 products of alternate k-iterations
+  // and one "correction" accumulator for every cross product.  The tensor core aligns and TRUNCATES addends to
+  // the accumulator's exponent on every MMA, a biased error ~2^-25 |acc| per instruction; keeping the 2^-8-scaled
+  // cross terms apart and halving the chain length of the main sums brings the result back to fp32-FMA quality.
+  // The epilogue adds the three in fp32.
+  constexpr int TMEM_COLS = BN == 64 ? 256 : 512;   // 3 * BN rounded up to a power of two
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][nsplit A tiles][nsplit W tiles] (1024-aligned), then barriers
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      uint32_t accumulate = 0;
+      uint32_t acc_main[2] = {0, 0}, acc_corr = 0;
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -195,10 +200,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           for (int i = 0; i <= sum; ++i) {
             const int j = sum - i;
             const uint32_t a_t = a_base + i * A_TILE_BYTES, w_t = w_base + j * W_TILE_BYTES;
+            const bool corr = sum > 0;
+            const uint32_t d = tmem_base + (corr ? 2 * BN : (it & 1) * BN);
+            uint32_t& flag = corr ? acc_corr : acc_main[it & 1];
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              tc_mma_bf16(tmem_base, umma_desc(a_t + k * UMMA_K * 2), umma_desc(w_t + k * UMMA_K * 2), IDESC, accumulate);
-              accumulate = 1;
+              tc_mma_bf16(d, umma_desc(a_t + k * UMMA_K * 2), umma_desc(w_t + k * UMMA_K * 2), IDESC, flag);
+              flag = 1;
             }
           }
         }
@@ -225,14 +233,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t acc[32];
-      __syncwarp();                                                                // .sync.aligned: whole warp converged
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, acc);
-      const int n = n0 + c0;
-      if (row_ok && n < p.cout) {
       float v[32];
-      const bool full = n + 32 <= p.cout;
+      const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      __syncwarp();                                                                // .sync.aligned: whole warp converged
+      tmem_ld32(lane_col, acc);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      if (n_iter > 1) {                                                            // second main accumulator in use
+        tmem_ld32(lane_col + BN, acc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+      }
+      if (p.nsplit > 1) {                                                          // cross-product accumulator
+        tmem_ld32(lane_col + 2 * BN, acc);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+      }
+      const int n = n0 + c0;
+      if (row_ok && n < p.cout) {
+      const bool full = n + 32 <= p.cout;
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (full || n + j < p.cout) v[j] += __ldg(p.bias + n + j);
