@@ -315,19 +315,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fp32 -> bf16 planes.  One CTA row-block per (clip, row tile): no per-element index arithmetic, 16-byte loads,
+// 8-byte stores.  VEC path needs ch % 4 == 0 and 16-byte aligned rows.
+template <bool VEC>
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long x_bs, int ldx, int rows,
                                                          int ch, __nv_bfloat16* __restrict__ out, long long o_ps,
-                                                         long long o_bs, int ldo, int nsplit, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ch);
-    const long long br = i / ch;
-    const int r = (int)(br % rows);
-    const long long b = br / rows;
-    const float v = x[b * x_bs + (long long)r * ldx + c];
-    __nv_bfloat16 pp[3];
-    split3(v, nsplit, pp);
-    __nv_bfloat16* o = out + b * o_bs + (long long)r * ldo + c;
-    for (int pl = 0; pl < nsplit; ++pl) o[(long long)pl * o_ps] = pp[pl];
+                                                         long long o_bs, int ldo, int nsplit) {
+  const int b = blockIdx.y;
+  const float* __restrict__ xb = x + (long long)b * x_bs;
+  __nv_bfloat16* __restrict__ ob = out + (long long)b * o_bs;
+  if (VEC) {
+    const int ch4 = ch >> 2;
+    const long long total = (long long)rows * ch4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / ch4), c4 = (int)(i - (long long)r * ch4);
+      const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * ldx + 4 * c4);
+      __nv_bfloat16 a[3], bq[3], c[3], d[3];
+      split3(v.x, nsplit, a); split3(v.y, nsplit, bq); split3(v.z, nsplit, c); split3(v.w, nsplit, d);
+      __nv_bfloat16* o = ob + (long long)r * ldo + 4 * c4;
+      for (int pl = 0; pl < nsplit; ++pl) {
+        __align__(8) __nv_bfloat16 h[4] = {a[pl], bq[pl], c[pl], d[pl]};
+        *reinterpret_cast<uint2*>(o + (long long)pl * o_ps) = *reinterpret_cast<const uint2*>(h);
+      }
+    }
+  } else {
+    const long long total = (long long)rows * ch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / ch), c = (int)(i - (long long)r * ch);
+      __nv_bfloat16 pp[3];
+      split3(xb[(long long)r * ldx + c], nsplit, pp);
+      __nv_bfloat16* o = ob + (long long)r * ldo + c;
+      for (int pl = 0; pl < nsplit; ++pl) o[(long long)pl * o_ps] = pp[pl];
+    }
   }
 }
 
@@ -399,12 +418,13 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   PM_REQUIRE(!out_bf16 || ldob >= cout);
   PM_REQUIRE(!residual || ldr >= cout);
 
-  const int BNsel = cout <= 64 ? 64 : 128;
-  PM_REQUIRE(w_rows % BNsel == 0);
-
   int R = 128;
   if (rows_out <= 64 && batch > 1) { R = 16; while (R < rows_out) R <<= 1; }
   const int NB = 128 / R;
+  // N tile: 128 columns unless that leaves most of the 148 SMs idle (the M = 2048 transformer GEMMs), then 64
+  int BNsel = cout <= 64 ? 64 : 128;
+  if (BNsel == 128 && (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB) * pm_cdiv(cout, 128) < 120) BNsel = 64;
+  PM_REQUIRE(w_rows % BNsel == 0);
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
@@ -441,12 +461,17 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
 extern "C" int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,
                              uint16_t* out, long long o_ps, long long o_bs, int ldo, int nsplit, void* stream) {
   PM_REQUIRE(x && out && batch >= 0 && rows >= 0 && ch > 0 && ldx >= ch && ldo >= ch && nsplit >= 1 && nsplit <= 3);
-  const long long total = (long long)batch * rows * ch;
-  if (total == 0) return PM_OK;
-  long long g = (total + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  split_bf16_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch,
-                                                                  reinterpret_cast<__nv_bfloat16*>(out), o_ps, o_bs, ldo,
-                                                                  nsplit, total);
+  if ((long long)batch * rows == 0) return PM_OK;
+  PM_REQUIRE(batch <= 65535);
+  const bool vec = (ch & 3) == 0 && (ldx & 3) == 0 && (x_bs & 3) == 0 && (ldo & 3) == 0 && (o_bs & 3) == 0 &&
+                   (o_ps & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  const long long work = (long long)rows * (vec ? ch / 4 : ch);
+  long long gx = (work + 255) / 256;
+  const long long cap = batch >= 148 * 4 ? 1 : (148 * 8 + batch - 1) / batch;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, batch);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (vec) split_bf16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+  else split_bf16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
   PM_LAUNCH_CHECK();
 }

@@ -62,6 +62,48 @@ def get_precision() -> str:
     return next(k for k, v in PRECISIONS.items() if v == _STATE["nsplit"])
 
 
+def _record_stream(obj, stream):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream)
+
+
+class _Fork:
+    """Run independent branches of the schedule on side CUDA streams and join them on the current stream
+    (the face decoder || the body stack, the three refine decoders, the four VQ part decoders).  The M = 2048
+    GEMMs of one branch fill only ~100 of the 148 SMs; overlapping branches fills the rest.  Works inside
+    CUDA-graph capture (event waits become graph edges).  Sequential when there is no CUDA device (tests)."""
+
+    def __init__(self, n_side):
+        self.n_side, self.streams = n_side, None
+
+    def run(self, fns):
+        if not torch.cuda.is_available() or len(fns) == 1:
+            return [fn() for fn in fns]
+        if self.streams is None:
+            self.streams = [torch.cuda.Stream() for _ in range(self.n_side)]
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        results = [None] * len(fns)
+        for i in range(1, len(fns)):
+            st = self.streams[i - 1]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                results[i] = fns[i]()
+        results[0] = fns[0]()
+        for i in range(1, len(fns)):
+            cur.wait_stream(self.streams[i - 1])
+            _record_stream(results[i], cur)
+        return results
+
+
 class _Conv:
     """One Conv1d / Linear: fp32 tap-major weights (taps, cout, cin) + lazily packed bf16 planes."""
     __slots__ = ("w", "b", "stride", "pad", "_packed")
@@ -267,20 +309,25 @@ class EmageEngine:
         self.out_proj["face"] = _Linear(sd, "face_out_proj")
         self.cls = {p: _MLP(sd, "motion_cls_" + p) for p in PARTS[1:]}
         self.cls["face"] = _MLP(sd, "face_cls")
+        self._fork_branch, self._fork_parts, self._fork_audio = _Fork(1), _Fork(2), _Fork(1)
 
     # ------------------------------------------------------------------------------------------------
     def audio_phase(self, audio, offset, a_ws, windows, n_samples, t):
         """Everything that depends on audio only, for `windows` equally long slices per clip.
         Returns window-major tensors: face memory audio part (w*bs, t, E), body cross-attn K|V of the
         8 layers (list of (w*bs, tk, 2E))."""
-        a_face = self.wav_face(audio, offset, a_ws, windows, n_samples)
-        a_body = self.wav_body(audio, offset, a_ws, windows, n_samples)
-        if a_face.shape[1] < t:
-            raise ValueError(f"audio slice yields {a_face.shape[1]} frames < {t} motion frames")
-        a_face = a_face[:, :t]                     # M.py:278-281 (the body stream is never truncated)
-        mem_face = self.face_mem_audio(a_face)
-        mem_body = self.body_mem(a_body)
-        kv = [layer.project_memory(mem_body) for layer in self.cross]
+        if wav_out_len(n_samples) < t:
+            raise ValueError(f"audio slice yields {wav_out_len(n_samples)} frames < {t} motion frames")
+
+        def face():
+            a_face = self.wav_face(audio, offset, a_ws, windows, n_samples)
+            return self.face_mem_audio(a_face[:, :t])      # M.py:278-281 (the body stream is never truncated)
+
+        def body():
+            mem_body = self.body_mem(self.wav_body(audio, offset, a_ws, windows, n_samples))
+            return [layer.project_memory(mem_body) for layer in self.cross]
+
+        kv, mem_face = self._fork_audio.run([body, face])
         return mem_face, kv
 
     def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body):
@@ -290,33 +337,44 @@ class EmageEngine:
         E = self.E
         spk_f, spk_b = speaker_id_rows
         hint = self.motion_encoder(win_in)                                              # M.py:271
-        hint_body, hint_face = self.hint_body(hint), self.hint_face(hint)
-        out = {}
-        # face branch, M.py:288-294
-        mem_f = self.face_mem_hint(hint_face, residual=mem_face_audio)
-        x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
-        for layer in self.face_dec:
-            x = layer(x, layer.project_memory(mem_f))
-        out["rec_face"] = self.out_proj["face"](x)
-        out["cls_face"] = self.cls["face"](out["rec_face"])
-        # body branch, M.py:297-330
-        x = ops.add_rows(self.moton_proj(hint_body), self.pe, spk_b, ops.ROW_PE, ops.ROW_SPK, bs, t, E)
-        fea = self.self_enc(x)
-        fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
-        x = fea
-        for layer, kv in zip(self.cross, kv_body):
-            x = layer(x, kv)
-        fea = ops.add2(fea, x)
-        lat = {p: self.to_latent[p](fea) for p in PARTS[1:]}
-        others = {"upper": ("hands", "lower"), "hands": ("upper", "lower"), "lower": ("upper", "hands")}
-        for p in PARTS[1:]:
-            a, b = others[p]
-            layer = self.refine[p]
-            tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E)
-            refine = layer(tgt, layer.project_memory(ops.add2(lat[a], lat[b])))
-            out["rec_" + p] = self.out_proj[p](ops.add2(lat[p], refine))
-            out["cls_" + p] = self.cls[p](out["rec_" + p])
-        return out
+
+        def face_branch():                                                              # M.py:288-294
+            hint_face = self.hint_face(hint)
+            mem_f = self.face_mem_hint(hint_face, residual=mem_face_audio)
+            x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
+            for layer in self.face_dec:
+                x = layer(x, layer.project_memory(mem_f))
+            rec = self.out_proj["face"](x)
+            return {"rec_face": rec, "cls_face": self.cls["face"](rec)}
+
+        def body_branch():                                                              # M.py:297-330
+            hint_body = self.hint_body(hint)
+            x = ops.add_rows(self.moton_proj(hint_body), self.pe, spk_b, ops.ROW_PE, ops.ROW_SPK, bs, t, E)
+            fea = self.self_enc(x)
+            fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
+            x = fea
+            for layer, kv in zip(self.cross, kv_body):
+                x = layer(x, kv)
+            fea = ops.add2(fea, x)
+            lat = {p: self.to_latent[p](fea) for p in PARTS[1:]}
+            others = {"upper": ("hands", "lower"), "hands": ("upper", "lower"), "lower": ("upper", "hands")}
+
+            def refine(p):
+                a, b = others[p]
+                layer = self.refine[p]
+                tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E)
+                r = layer(tgt, layer.project_memory(ops.add2(lat[a], lat[b])))
+                rec = self.out_proj[p](ops.add2(lat[p], r))
+                return {"rec_" + p: rec, "cls_" + p: self.cls[p](rec)}
+
+            out = {}
+            for d in self._fork_parts.run([lambda p=p: refine(p) for p in PARTS[1:]]):
+                out.update(d)
+            return out
+
+        body, face = self._fork_branch.run([body_branch, face_branch])
+        body.update(face)
+        return body
 
     def speaker_rows(self, speaker_id):
         """nn.Embedding lookup of the (bs,1) speaker ids (M.py:285-286): pure row gather."""
@@ -344,6 +402,7 @@ class VQEngine:
             self.global_enc = _ConvStack(sds["global"], "encoder", "encoder", n)
             self.global_dec = _ConvStack(sds["global"], "decoder", "decoder", n)
         self.device = self.codebook["face"].device
+        self._fork = _Fork(3)
 
     def part_decode(self, p, index=None, latent=None):
         """EmageVQVAEConv.decode / decode_from_latent (M.py:56-70) -> (pose features, indices)."""
@@ -355,10 +414,9 @@ class VQEngine:
         """index/latent: dicts part -> tensor or None.  Returns the reference's 4-key dict (M.py:193)."""
         shape = next(t.shape[:2] for t in list(index.values()) + list(latent.values()) if t is not None)
         bs, t = int(shape[0]), int(shape[1])
-        feats = {}
-        for p in PARTS:
-            if index.get(p) is not None or latent.get(p) is not None:
-                feats[p], _ = self.part_decode(p, index.get(p), latent.get(p))
+        todo = [p for p in PARTS if index.get(p) is not None or latent.get(p) is not None]
+        done = self._fork.run([lambda p=p: self.part_decode(p, index.get(p), latent.get(p))[0] for p in todo])
+        feats = dict(zip(todo, done))
         expression, aa, m4 = ops.pose_compose(feats.get("face"), feats.get("upper"), feats.get("hands"),
                                               feats.get("lower"), bs, t, self.device)
         trans = None

@@ -19,9 +19,12 @@ for r in csv.DictReader(lines):
 rows = rows[skip:]
 agg = defaultdict(lambda: [0, 0.0])
 for name, ns in rows:
-    short = re.sub(r"<.*", "", name.split("(")[0]).split("::")[-1]
-    if "tapgemm_tc_kernel" in name:
-        short += "<" + (re.search(r"tapgemm_tc_kernel<\(?int\)?(\d+)", name) or [0, "?"])[1] + ">"
+    head = name.replace("void ", "").replace("<unnamed>::", "")
+    m = re.match(r"([\w:]+)(<[\w, ]*>)?", head)
+    short = (m.group(1) + (m.group(2) or "")) if m else head[:40]
+    if short.startswith("at::"):
+        f = re.search(r"at::(\w+(?:Functor|_kernel_cuda|Copy\w*)[\w]*)", name[len(short):])
+        short = "torch:" + short.split("::")[-1].split("<")[0] + ("/" + f.group(1) if f else "")
     agg[short][0] += 1
     agg[short][1] += ns
 total = sum(v[1] for v in agg.values())
