@@ -208,11 +208,8 @@ def run_gpu(args):
     # weights: rank 0's checkpoint is the job's checkpoint; one NCCL broadcast per tensor at load
     model, vqm = build_product(seed=0, device=dev)
     if world > 1:
-        for m in (model, vqm):
-            for t in list(m.parameters()) + list(m.buffers()):
-                dist.broadcast(t.data, src=0)
-        model._invalidate()
-        vqm._engine = None
+        from pantomatrix_b200.sharding import broadcast_checkpoint
+        broadcast_checkpoint(model, vqm, src=0)
 
     clips = CLIPS_PER_GPU
     host_audio = torch.from_numpy(synth_audio(clips, N_SAMPLES, 1234 + rank)).pin_memory()

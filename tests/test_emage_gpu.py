@@ -183,15 +183,22 @@ def test_teacher_forced_windows_and_free_run_vs_oracle(product, ckpt):
                  frames=None if ok.all() else ok, raw=want_pred["_raw"])
 
 
-def test_baseline_config_batch32(product, ckpt):
-    """BASELINE configs[1]: 32 clips x 300 frames.  Index agreement must be total on this seeded input;
-    size-independent properties: emitted length, unit-norm rot6d rows, trans integrates its velocities."""
+@pytest.mark.parametrize("precision", ["fp32", "bf16x6"])
+def test_baseline_config_batch32(product, ckpt, precision):
+    """BASELINE configs[1]: 32 clips x 300 frames, free-running, for the exact fp32 engine and the default
+    tensor-core mode.  Index agreement must be total on this seeded input; size-independent properties:
+    emitted length, unit-norm orthogonal rot6d rows."""
+    from pantomatrix_b200.emage_audio import engine
     from pantomatrix_b200.pipeline import generate
     model, vqm = product
     sd, cfg, vq = ckpt
     bs = 32
     audio = torch.from_numpy(synth_audio(bs, 160000, 1234))
-    lat, pred = generate(model, vqm, audio.cuda())
+    engine.set_precision(precision)
+    try:
+        lat, pred = generate(model, vqm, audio.cuda())
+    finally:
+        engine.set_precision("fp32")
     assert lat["rec_face"].shape == (bs, 300, 256) and pred["motion_axis_angle"].shape == (bs, 300, 165)
     m4 = pred["all_motion4inference"][:, :, :330].reshape(bs, 300, 55, 2, 3)
     assert (m4.norm(dim=-1) - 1).abs().max() < 1e-4 and (m4[..., 0, :] * m4[..., 1, :]).sum(-1).abs().max() < 1e-4
