@@ -13,6 +13,9 @@
  *     batch stride `*_bs` in elements (lets callers pass column slices / overlapping windows)
  *   - `stream` is a cudaStream_t passed as void*; nothing allocates, nothing synchronises
  *   - return 0 = ok, <0 = PM_E* argument error, >0 = cudaError_t from the launch
+ *   - optional split-bf16 output (`planes`, p_ps, p_ld, p_nsplit): the producer also (or only, when its fp32
+ *     `out` is NULL) writes its result as p_nsplit bf16 planes (x ~ p0+p1+p2, plane stride p_ps, row stride
+ *     p_ld elements): the A operand format of pm_tapgemm_tc, so no separate conversion pass is needed
  */
 #ifndef PM_EMAGE_H
 #define PM_EMAGE_H
@@ -76,29 +79,34 @@ int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_ws, int batc
 /* ---- LayerNorm(x + r) * gamma + beta over the last dim (r nullable): post-norm residual of
  * nn.TransformerEncoderLayer / DecoderLayer (M.py:238-250), eps 1e-5.  ch must be a multiple of 128 <= 1024 */
 int pm_add_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta,
-                         float* out, long long rows, int ch, float eps, void* stream);
+                         float* out, long long rows, int ch, float eps,
+                         uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- multi-head attention core, no masks: softmax(Q K^T / sqrt(hd)) V for Tq,Tk <= 64, hd = 192 ----
  * Q/K/V rows are (b*T + t) with row strides ldq/ldk/ldv; head h occupies columns [h*hd,(h+1)*hd).
  * Replaces scaled_dot_product_attention inside nn.MultiheadAttention (M.py:238-250 layers). */
 int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
-                     float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim, void* stream);
+                     float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim,
+                     uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- broadcast adds: out[b,t,:] = ((x[b,t,:] + first) + second), each of first/second chosen by code:
  * 0 = nothing, 1 = pe[t,:] (PeriodicPositionalEncoding P.py:341-343), 2 = spk[b,:] (speaker embedding
  * row repeated over t, M.py:285-286).  x nullable (treated as 0).  Preserves the reference's add order
  * (M.py:291,298-299,307-308,320-322). */
 int pm_add_rows_f32(const float* x, const float* pe, const float* spk, int first, int second,
-                    float* out, int batch, int rows, int ch, void* stream);
-/* out = a + b (M.py:312,320-325) */
-int pm_add2_f32(const float* a, const float* b, float* out, long long n, void* stream);
+                    float* out, int batch, int rows, int ch,
+                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
+/* out = a + b over n elements viewed as rows of `ch` (M.py:312,320-325) */
+int pm_add2_f32(const float* a, const float* b, float* out, long long n, int ch,
+                uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- window assembly (M.py:384-391 and 267-268 fused): builds one window's motion-encoder input.
  * motion/mask: (batch, total_len, ch) full-sequence tensors; seed: (batch, pre, ch) decoded last frames.
  * For frame f<pre: v = mask==0 ? motion : seed, window mask forced 0; else v = motion, m = mask.
  * out = (m == 1) ? mask_embedding[c] : v. */
 int pm_window_input_f32(const float* motion, const float* mask, const float* seed, const float* mask_embedding,
-                        float* out, int batch, int total_len, int start, int win_len, int pre, int ch, void* stream);
+                        float* out, int batch, int total_len, int start, int win_len, int pre, int ch,
+                        uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- VQ ------------------------------------------------------------------------------------------ */
 /* index = argmin_k ( |z|^2 + |e_k|^2 - 2 z.e_k ), first minimum wins: EmageVQVAEConv.decode_from_latent
@@ -110,7 +118,7 @@ int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, cons
 int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream);
 /* out[r,:] = codebook[index[r],:]: Quantizer.get_codebook_entry P.py:166-170 */
 int pm_gather_rows_f32(const float* codebook, const long long* index, long long rows, int ch,
-                       float* out, void* stream);
+                       float* out, uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 /* |e_k|^2 per codebook row (done once at pack time) */
 int pm_row_sqnorm_f32(const float* x, int rows, int ch, float* out, void* stream);
 

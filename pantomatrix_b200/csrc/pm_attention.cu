@@ -14,7 +14,7 @@ constexpr int NT = 256;
 __global__ void __launch_bounds__(NT) attention_f32_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
     const float* __restrict__ V, int ldv, float* __restrict__ O, int ldo,
-    int heads, int tq, int tk, float scale) {
+    int heads, int tq, int tk, float scale, PmPlanes P) {
   extern __shared__ float smem[];
   float* Qs = smem;                    // [TMAX][HDP]
   float* Ks = Qs + TMAX * HDP;         // [TMAX][HDP]
@@ -107,9 +107,15 @@ __global__ void __launch_bounds__(NT) attention_f32_kernel(
     for (int a = 0; a < 4; ++a) {
       const int r = tr * 4 + a;
       if (r >= tq) continue;
-      float* o = O + (long long)(b * tq + r) * ldo + h * HD;
+      if (O) {
+        float* o = O + (long long)(b * tq + r) * ldo + h * HD;
 #pragma unroll
-      for (int m = 0; m < 12; ++m) o[tc + 16 * m] = acc[a][m];
+        for (int m = 0; m < 12; ++m) o[tc + 16 * m] = acc[a][m];
+      }
+      if (P.ptr) {
+#pragma unroll
+        for (int m = 0; m < 12; ++m) pm_store_planes(P, (long long)b * tq + r, h * HD + tc + 16 * m, acc[a][m]);
+      }
     }
   }
 }
@@ -120,8 +126,10 @@ constexpr size_t kSmemBytes = (size_t)(2 * TMAX * HDP + TMAX * HD + TMAX * (TMAX
 
 extern "C" int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                                 float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim,
-                                void* stream) {
-  PM_REQUIRE(Q && K && V && O && batch >= 0 && heads > 0);
+                                uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE(Q && K && V && (O || planes) && batch >= 0 && heads > 0);
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, heads * head_dim, false));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (head_dim != HD || tq > TMAX || tk > TMAX || tq <= 0 || tk <= 0) return PM_EUNSUPPORTED;
   PM_REQUIRE((ldq & 3) == 0 && (ldk & 3) == 0 && (ldv & 3) == 0);
   if (batch == 0) return PM_OK;
@@ -133,6 +141,6 @@ extern "C" int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk
     configured = true;
   }
   attention_f32_kernel<<<batch * heads, NT, kSmemBytes, (cudaStream_t)stream>>>(
-      Q, ldq, K, ldk, V, ldv, O, ldo, heads, tq, tk, 1.0f / sqrtf((float)head_dim));
+      Q, ldq, K, ldk, V, ldv, O, ldo, heads, tq, tk, 1.0f / sqrtf((float)head_dim), P);
   PM_LAUNCH_CHECK();
 }

@@ -1,5 +1,6 @@
 // Shared helpers for the EMAGE hot-path kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,4 +40,45 @@ __device__ __forceinline__ float pm_warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- split-bf16 planes (operands of the tcgen05 engine): x ~ p0 + p1 + p2, round-to-nearest each ----
+struct PmPlanes {
+  __nv_bfloat16* ptr;   // plane 0, element (row 0, channel 0); nullptr = no plane output
+  long long ps;         // plane stride (elements)
+  int ld;               // row stride (elements)
+  int nsplit;           // 1..3
+};
+
+__device__ __forceinline__ void pm_split3(float v, __nv_bfloat16 (&p)[3]) {
+  p[0] = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(p[0]);
+  p[1] = __float2bfloat16_rn(r);
+  r -= __bfloat162float(p[1]);
+  p[2] = __float2bfloat16_rn(r);
+}
+
+__device__ __forceinline__ void pm_store_planes(const PmPlanes& P, long long row, int c, float v) {
+  __nv_bfloat16 pp[3];
+  pm_split3(v, pp);
+  __nv_bfloat16* o = P.ptr + row * P.ld + c;
+  for (int pl = 0; pl < P.nsplit; ++pl) o[(long long)pl * P.ps] = pp[pl];
+}
+
+// 4 consecutive channels, c % 4 == 0, ld % 4 == 0, ps % 4 == 0, 8-byte aligned base
+__device__ __forceinline__ void pm_store_planes4(const PmPlanes& P, long long row, int c, float4 v) {
+  __nv_bfloat16 a[3], b[3], cc[3], d[3];
+  pm_split3(v.x, a); pm_split3(v.y, b); pm_split3(v.z, cc); pm_split3(v.w, d);
+  __nv_bfloat16* o = P.ptr + row * P.ld + c;
+  for (int pl = 0; pl < P.nsplit; ++pl) {
+    __align__(8) __nv_bfloat16 h[4] = {a[pl], b[pl], cc[pl], d[pl]};
+    *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = *reinterpret_cast<const uint2*>(h);
+  }
+}
+
+static inline bool pm_planes_ok(const void* ptr, long long ps, int ld, int nsplit, int ch, bool vec4) {
+  if (!ptr) return true;
+  if (nsplit < 1 || nsplit > 3 || ld < ch) return false;
+  if (vec4 && ((ld & 3) || (ps & 3) || (reinterpret_cast<uintptr_t>(ptr) & 7))) return false;
+  return true;
 }

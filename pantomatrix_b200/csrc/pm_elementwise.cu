@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) wav_stem_kernel(
 template <int VEC>   // float4 chunks per lane: ch = VEC * 128
 __global__ void __launch_bounds__(256) add_layernorm_kernel(
     const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float* __restrict__ out, long long rows, float eps) {
+    const float* __restrict__ beta, float* __restrict__ out, long long rows, float eps, PmPlanes P) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(
   const float rstd = rsqrtf(pm_warp_sum(q) * (1.f / CH) + eps);
   const float4* __restrict__ g4 = reinterpret_cast<const float4*>(gamma);
   const float4* __restrict__ b4 = reinterpret_cast<const float4*>(beta);
-  float4* __restrict__ o4 = reinterpret_cast<float4*>(out + row * CH);
+  float4* __restrict__ o4 = out ? reinterpret_cast<float4*>(out + row * CH) : nullptr;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(
     o.y = (v[i].y - mean) * rstd * g.y + bb.y;
     o.z = (v[i].z - mean) * rstd * g.z + bb.z;
     o.w = (v[i].w - mean) * rstd * g.w + bb.w;
-    o4[lane + 32 * i] = o;
+    if (o4) o4[lane + 32 * i] = o;
+    if (P.ptr) pm_store_planes4(P, row, (lane + 32 * i) * 4, o);
   }
 }
 
@@ -105,7 +106,7 @@ __device__ __forceinline__ float4 pick_row(int code, const float* pe, const floa
 
 __global__ void __launch_bounds__(256) add_rows_kernel(
     const float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ spk,
-    int first, int second, float* __restrict__ out, int batch, int rows, int ch) {
+    int first, int second, float* __restrict__ out, int batch, int rows, int ch, PmPlanes P) {
   const int ch4 = ch >> 2;
   const long long total = (long long)batch * rows * ch4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -122,19 +123,24 @@ __global__ void __launch_bounds__(256) add_rows_kernel(
       const float4 a = pick_row(second, pe, spk, b, t, ch, c4);
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
-    reinterpret_cast<float4*>(out)[i] = v;
+    if (out) reinterpret_cast<float4*>(out)[i] = v;
+    if (P.ptr) pm_store_planes4(P, bt, c4 * 4, v);
   }
 }
 
+// rows x ch (ch % 4 == 0 when planes are requested; otherwise the tensor is treated as one flat row)
 __global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                   float* __restrict__ out, long long n4, long long n) {
+                                                   float* __restrict__ out, long long n4, long long n, int ch4,
+                                                   PmPlanes P) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
-    reinterpret_cast<float4*>(out)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    const float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    if (out) reinterpret_cast<float4*>(out)[i] = o;
+    if (P.ptr) pm_store_planes4(P, i / ch4, (int)(i % ch4) * 4, o);
   }
-  // scalar tail (n not a multiple of 4)
-  if (blockIdx.x == 0) {
+  // scalar tail (n not a multiple of 4; never with planes)
+  if (blockIdx.x == 0 && out) {
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = a[i] + b[i];
   }
 }
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, 
 __global__ void __launch_bounds__(256) window_input_kernel(
     const float* __restrict__ motion, const float* __restrict__ mask, const float* __restrict__ seed,
     const float* __restrict__ mask_embedding, float* __restrict__ out,
-    int batch, int total_len, int start, int win_len, int pre, int ch) {
+    int batch, int total_len, int start, int win_len, int pre, int ch, PmPlanes P) {
   const long long total = (long long)batch * win_len * ch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -156,7 +162,9 @@ __global__ void __launch_bounds__(256) window_input_kernel(
       if (m != 0.f) v = seed[((long long)b * pre + f) * ch + c];
       m = 0.f;
     }
-    out[i] = (m == 1.f) ? mask_embedding[c] : v;   // M.py:267-268
+    const float o = (m == 1.f) ? mask_embedding[c] : v;   // M.py:267-268
+    if (out) out[i] = o;
+    if (P.ptr) pm_store_planes(P, bf, c, o);
   }
 }
 
@@ -186,50 +194,63 @@ extern "C" int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_w
 }
 
 extern "C" int pm_add_layernorm_f32(const float* x, const float* r, const float* gamma, const float* beta,
-                                    float* out, long long rows, int ch, float eps, void* stream) {
-  PM_REQUIRE(x && gamma && beta && out && rows >= 0);
+                                    float* out, long long rows, int ch, float eps,
+                                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE(x && gamma && beta && (out || planes) && rows >= 0);
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (rows == 0) return PM_OK;
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   cudaStream_t st = (cudaStream_t)stream;
   switch (ch) {
-    case 256: add_layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
-    case 512: add_layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
-    case 768: add_layernorm_kernel<6><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
-    case 1024: add_layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps); break;
+    case 256: add_layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
+    case 512: add_layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
+    case 768: add_layernorm_kernel<6><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
+    case 1024: add_layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
     default: return PM_EUNSUPPORTED;
   }
   PM_LAUNCH_CHECK();
 }
 
 extern "C" int pm_add_rows_f32(const float* x, const float* pe, const float* spk, int first, int second,
-                               float* out, int batch, int rows, int ch, void* stream) {
-  PM_REQUIRE(out && batch >= 0 && rows >= 0 && ch > 0 && (ch & 3) == 0);
+                               float* out, int batch, int rows, int ch,
+                               uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE((out || planes) && batch >= 0 && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   PM_REQUIRE(first >= 0 && first <= 2 && second >= 0 && second <= 2);
   PM_REQUIRE((first != 1 && second != 1) || pe);
   PM_REQUIRE((first != 2 && second != 2) || spk);
   const long long total = (long long)batch * rows * (ch >> 2);
   if (total == 0) return PM_OK;
   add_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, spk, first, second, out,
-                                                                        batch, rows, ch);
+                                                                        batch, rows, ch, P);
   PM_LAUNCH_CHECK();
 }
 
-extern "C" int pm_add2_f32(const float* a, const float* b, float* out, long long n, void* stream) {
-  PM_REQUIRE(a && b && out && n >= 0);
+extern "C" int pm_add2_f32(const float* a, const float* b, float* out, long long n, int ch,
+                           uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE(a && b && (out || planes) && n >= 0);
+  PM_REQUIRE(!planes || (ch > 0 && (ch & 3) == 0 && n % ch == 0));
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (n == 0) return PM_OK;
-  add2_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n);
+  add2_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n, planes ? ch / 4 : 1, P);
   PM_LAUNCH_CHECK();
 }
 
 extern "C" int pm_window_input_f32(const float* motion, const float* mask, const float* seed,
                                    const float* mask_embedding, float* out, int batch, int total_len,
-                                   int start, int win_len, int pre, int ch, void* stream) {
-  PM_REQUIRE(motion && mask && mask_embedding && out && (seed || pre == 0));
+                                   int start, int win_len, int pre, int ch,
+                                   uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE(motion && mask && mask_embedding && (out || planes) && (seed || pre == 0));
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, false));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   PM_REQUIRE(batch >= 0 && win_len >= 0 && start >= 0 && start + win_len <= total_len && pre >= 0 && ch > 0);
   const long long total = (long long)batch * win_len * ch;
   if (total == 0) return PM_OK;
   window_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch);
+      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, P);
   PM_LAUNCH_CHECK();
 }

@@ -16,7 +16,6 @@
 //                            and/or bf16 split planes for the next GEMM
 // Contract and reference call sites: include/pm_emage.h (pm_tapgemm_tc).
 #include <cuda.h>
-#include <cuda_bf16.h>
 
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
@@ -105,15 +104,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void split3(float v, int nsplit, __nv_bfloat16 (&p)[3]) {
-  p[0] = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(p[0]);
-  p[1] = __float2bfloat16_rn(r);
-  r -= __bfloat162float(p[1]);
-  p[2] = __float2bfloat16_rn(r);
-  (void)nsplit;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -289,7 +279,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             __nv_bfloat16 pp[3];
-            split3(v[j], p.out_nsplit, pp);
+            pm_split3(v[j], pp);
             h[j] = pp[pl];
           }
           if (vec_b && full) {
@@ -331,7 +321,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
       const int r = (int)(i / ch4), c4 = (int)(i - (long long)r * ch4);
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * ldx + 4 * c4);
       __nv_bfloat16 a[3], bq[3], c[3], d[3];
-      split3(v.x, nsplit, a); split3(v.y, nsplit, bq); split3(v.z, nsplit, c); split3(v.w, nsplit, d);
+      pm_split3(v.x, a); pm_split3(v.y, bq); pm_split3(v.z, c); pm_split3(v.w, d);
       __nv_bfloat16* o = ob + (long long)r * ldo + 4 * c4;
       for (int pl = 0; pl < nsplit; ++pl) {
         __align__(8) __nv_bfloat16 h[4] = {a[pl], bq[pl], c[pl], d[pl]};
@@ -343,7 +333,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const int r = (int)(i / ch), c = (int)(i - (long long)r * ch);
       __nv_bfloat16 pp[3];
-      split3(xb[(long long)r * ldx + c], nsplit, pp);
+      pm_split3(xb[(long long)r * ldx + c], pp);
       __nv_bfloat16* o = ob + (long long)r * ldo + c;
       for (int pl = 0; pl < nsplit; ++pl) o[(long long)pl * o_ps] = pp[pl];
     }

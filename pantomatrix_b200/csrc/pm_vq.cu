@@ -125,13 +125,15 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ codebook,
                                                           const long long* __restrict__ index, long long rows,
-                                                          int ch4, float* __restrict__ out) {
+                                                          int ch4, float* __restrict__ out, PmPlanes P) {
   const long long total = rows * ch4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ch4;
     const int c4 = (int)(i % ch4);
-    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(codebook)[index[r] * ch4 + c4];
+    const float4 v = reinterpret_cast<const float4*>(codebook)[index[r] * ch4 + c4];
+    if (out) reinterpret_cast<float4*>(out)[i] = v;
+    if (P.ptr) pm_store_planes4(P, r, c4 * 4, v);
   }
 }
 
@@ -173,12 +175,15 @@ extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx
 }
 
 extern "C" int pm_gather_rows_f32(const float* codebook, const long long* index, long long rows, int ch,
-                                  float* out, void* stream) {
-  PM_REQUIRE(codebook && index && out && rows >= 0 && ch > 0 && (ch & 3) == 0);
+                                  float* out, uint16_t* planes, long long p_ps, int p_ld, int p_nsplit,
+                                  void* stream) {
+  PM_REQUIRE(codebook && index && (out || planes) && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (rows == 0) return PM_OK;
   long long g = (rows * (ch >> 2) + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  gather_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out);
+  gather_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
   PM_LAUNCH_CHECK();
 }
 

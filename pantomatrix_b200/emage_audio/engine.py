@@ -127,35 +127,71 @@ class _Conv:
             self._packed[nsplit] = ops.PackedW(w, nsplit)
         return self._packed[nsplit]
 
-    def __call__(self, x, act=ops.ACT_NONE, slope=0.0, residual=None, out=None):
+    def __call__(self, x, act=ops.ACT_NONE, slope=0.0, residual=None, out=None, want="f", out_slack=0):
+        """x: fp32 tensor, ops.Planes or ops.Act.  want: "f" (fp32 tensor returned), "p" (bf16 planes only) or
+        "fp" (both); with planes requested an ops.Act is returned.  In fp32 mode planes do not exist: the fp32
+        tensor is always produced and returned (wrapped in an Act when planes were asked for)."""
         ns = _STATE["nsplit"]
+        residual = _f32(residual)
         if ns == 0:
-            return ops.tapgemm(x, self.w, self.b, stride=self.stride, pad=self.pad, act=act, slope=slope,
-                               residual=residual, out=out)
-        batch, rows, cin = x.shape
+            y = ops.tapgemm(_f32(x), self.w, self.b, stride=self.stride, pad=self.pad, act=act, slope=slope,
+                            residual=residual, out=out)
+            return y if want == "f" else ops.Act(y, None)
         taps, cout, _ = self.w.shape
         s = self.stride
+        want_f, out_ns = "f" in want, (ns if "p" in want else 0)
         if s == 1:
+            a = _planes(x, ns)
+            batch, rows = a.batch, a.rows
             rows_out = rows + 2 * self.pad - taps + 1
-            flat = (taps == 1 and batch > 1 and x.is_contiguous() and (out is None or out.is_contiguous())
-                    and (residual is None or residual.is_contiguous()))
-            if out is None:
-                out = torch.empty(batch, rows_out, cout, device=x.device, dtype=torch.float32)
+            flat = (taps == 1 and batch > 1 and a.t.stride(1) == rows * a.t.stride(2)
+                    and (out is None or out.is_contiguous()) and (residual is None or residual.is_contiguous()))
+            if want_f and out is None:
+                out = torch.empty(batch, rows_out, cout, device=a.t.device, dtype=torch.float32)
             if flat:                                       # a Linear over all clips is one tall matrix
-                ops.tapgemm_tc(ops.split_bf16(x.view(1, batch * rows, cin), ns), self.packed(ns), self.b,
-                               rows_out=batch * rows, act=act, slope=slope, out=out.view(1, batch * rows, cout),
-                               residual=None if residual is None else residual.view(1, batch * rows, cout))
+                _, pl = ops.tapgemm_tc(a.flat(), self.packed(ns), self.b, rows_out=batch * rows, act=act, slope=slope,
+                                       want_f32=want_f, out=None if out is None else out.view(1, batch * rows, cout),
+                                       residual=None if residual is None else residual.view(1, batch * rows, cout),
+                                       out_nsplit=out_ns, out_slack=out_slack)
+                if pl is not None:                         # back to the (clips, rows) view
+                    pl = ops.Planes(pl.t.view(pl.t.shape[0], batch, rows, pl.t.shape[3]), rows, cout, pl.slack)
             else:
-                ops.tapgemm_tc(ops.split_bf16(x, ns), self.packed(ns), self.b, rows_out=rows_out, pad=self.pad,
-                               act=act, slope=slope, residual=residual, out=out)
-            return out
-        assert self.pad == 0 and x.is_contiguous()
+                _, pl = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, pad=self.pad, act=act, slope=slope,
+                                       residual=residual, want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack)
+            return out if want == "f" else ops.Act(out, pl)
+        assert self.pad == 0
+        a = _planes(x, ns, need_slack=s)
+        batch, rows, cin = a.batch, a.rows, a.ch
+        assert a.t.stride(2) == cin and a.t.stride(1) == rows * cin, "strided view needs dense (clips*rows, C) planes"
         rows_out = (rows - taps) // s + 1
-        a = ops.split_bf16(x, ns, slack_rows=s)
-        assert a.t.stride(2) == cin, "strided view needs unpadded channel rows"
-        o, _ = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, act=act, slope=slope, residual=residual,
-                              out=out, a_view=(-(-rows // s), s * cin, s * cin))
-        return o
+        o, pl = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, act=act, slope=slope, residual=residual,
+                               want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack,
+                               a_view=(-(-rows // s), s * cin, s * cin))
+        return o if want == "f" else ops.Act(o, pl)
+
+
+def _f32(x):
+    """The fp32 tensor of an activation (Act or plain tensor)."""
+    if isinstance(x, ops.Act):
+        assert x.f is not None, "this consumer needs the fp32 copy"
+        return x.f
+    return x
+
+
+def _planes(x, ns, need_slack=0):
+    """bf16 planes of an activation: reuse the producer's planes when present (and padded enough), else convert."""
+    if isinstance(x, ops.Planes):
+        assert x.slack >= need_slack
+        return x
+    if isinstance(x, ops.Act):
+        if x.p is not None and x.p.nsplit == ns and x.p.slack >= need_slack:
+            return x.p
+        x = x.f
+    return ops.split_bf16(x, ns, slack_rows=need_slack)
+
+
+def _ns():
+    return _STATE["nsplit"]
 
 
 class _Linear(_Conv):
@@ -171,8 +207,8 @@ class _MLP:
     def __init__(self, sd, p):
         self.fc1, self.fc2 = _Linear(sd, p + ".fc1"), _Linear(sd, p + ".fc2")
 
-    def __call__(self, x, out=None):
-        return self.fc2(self.fc1(x, act=ops.ACT_LEAKY, slope=0.1), out=out)
+    def __call__(self, x, out=None, want="f"):
+        return self.fc2(self.fc1(x, act=ops.ACT_LEAKY, slope=0.1, want="p"), out=out, want=want)
 
 
 class _ConvStack:
@@ -192,12 +228,16 @@ class _ConvStack:
                 self.steps.append(("conv", c(2 + 2 * i), True))
             self.steps.append(("conv", c(2 + 2 * n_layer), False))
 
-    def __call__(self, x):
-        for step in self.steps:
+    def __call__(self, x, want="f"):
+        """x: tensor / Act (a ResBlock needs its fp32 copy for the skip).  Intermediate activations travel as
+        fp32 + bf16 planes; only the last step honours `want`."""
+        last = len(self.steps) - 1
+        for i, step in enumerate(self.steps):
+            w = want if i == last else "fp"
             if step[0] == "conv":
-                x = step[1](x, act=ops.ACT_LEAKY if step[2] else ops.ACT_NONE, slope=0.2)
+                x = step[1](x, act=ops.ACT_LEAKY if step[2] else ops.ACT_NONE, slope=0.2, want=w)
             else:
-                x = step[2](step[1](x, act=ops.ACT_LEAKY, slope=0.2), residual=x)
+                x = step[2](step[1](x, act=ops.ACT_LEAKY, slope=0.2, want="p"), residual=x, want=w)
         return x
 
 
@@ -225,11 +265,13 @@ class _WavEncoder:
         w1, b1, wd, bd, stride, pad = self.stem
         y, sc = ops.wav_stem(audio, n, a_ws, bs, windows, n_samples, w1, b1, wd, bd, stride=stride, pad=pad,
                              slope=0.01, offset=offset)
-        x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc)
-        for conv1, conv2, ds in self.blocks[1:]:
-            y = conv1(x, act=ops.ACT_LEAKY, slope=0.01)
+        # block outputs feed the next block as (possibly strided) GEMM operand and as identity shortcut
+        x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want="fp", out_slack=8)
+        last = len(self.blocks) - 1
+        for i, (conv1, conv2, ds) in enumerate(self.blocks[1:], 1):
+            y = conv1(x, act=ops.ACT_LEAKY, slope=0.01, want="p")
             sc = ds(x) if ds is not None else x
-            x = conv2(y, act=ops.ACT_LEAKY, slope=0.01, residual=sc)
+            x = conv2(y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want="f" if i == last else "fp", out_slack=8)
         return x
 
 
@@ -257,26 +299,38 @@ class _Layer:
         self.norms = [(sd[f"{p}.norm{i + 1}.weight"].contiguous(), sd[f"{p}.norm{i + 1}.bias"].contiguous()) for i in range(n)]
 
     def project_memory(self, mem):
-        """K|V projection of a cross-attention memory (bs, tk, E) -> (bs, tk, 2E)."""
+        """K|V projection of a cross-attention memory (bs, tk, E) -> (bs, tk, 2E) fp32."""
         return self.ca.kv(mem)
 
-    def __call__(self, x, mem_kv=None):
-        bs, t, E = x.shape
+    def __call__(self, x, mem_kv=None, want="f"):
+        """x: fp32 tensor or Act(f, p) of (bs, t, E).  Returns the layer output in the requested form."""
+        ns = _ns()
+        xf = _f32(x)
+        bs, t, E = xf.shape
         hd = E // NHEAD
         qkv = self.sa.qkv(x).view(bs * t, 3 * E)
-        att = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], bs, NHEAD, t, t, hd).view(bs, t, E)
-        x = ops.add_layernorm(self.sa.out(att, residual=x), None, *self.norms[0])
+        att = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], bs, NHEAD, t, t, hd, nsplit=ns, f32=ns == 0)
+        x = ops.add_layernorm(self.sa.out(_view3(att, bs, t, E), residual=xf), None, *self.norms[0], nsplit=ns)
         k = 1
         if self.ca is not None:
             tk = mem_kv.shape[1]
             assert mem_kv.is_contiguous()
             kv = mem_kv.view(bs * tk, 2 * E)
             q = self.ca.q(x).view(bs * t, E)
-            att = ops.attention(q, kv[:, :E], kv[:, E:], bs, NHEAD, t, tk, hd).view(bs, t, E)
-            x = ops.add_layernorm(self.ca.out(att, residual=x), None, *self.norms[1])
+            att = ops.attention(q, kv[:, :E], kv[:, E:], bs, NHEAD, t, tk, hd, nsplit=ns, f32=ns == 0)
+            x = ops.add_layernorm(self.ca.out(_view3(att, bs, t, E), residual=_f32(x)), None, *self.norms[1], nsplit=ns)
             k = 2
-        h = self.l1(x, act=ops.ACT_RELU)
-        return ops.add_layernorm(self.l2(h, residual=x), None, *self.norms[k])
+        h = self.l1(x, act=ops.ACT_RELU, want="p")
+        want_ns = ns if "p" in want else 0
+        y = ops.add_layernorm(self.l2(h, residual=_f32(x)), None, *self.norms[k], nsplit=want_ns, f32="f" in want or want_ns == 0)
+        return y
+
+
+def _view3(att, bs, t, E):
+    """attention output (bs*t, E) fp32 tensor or Act -> (bs, t, E) view for the out-projection."""
+    if isinstance(att, ops.Act):
+        return ops.Act(None if att.f is None else att.f.view(bs, t, E), att.p)
+    return att.view(bs, t, E)
 
 
 class EmageEngine:
@@ -324,7 +378,7 @@ class EmageEngine:
             return self.face_mem_audio(a_face[:, :t])      # M.py:278-281 (the body stream is never truncated)
 
         def body():
-            mem_body = self.body_mem(self.wav_body(audio, offset, a_ws, windows, n_samples))
+            mem_body = self.body_mem(self.wav_body(audio, offset, a_ws, windows, n_samples), want="p" if _ns() else "f")
             return [layer.project_memory(mem_body) for layer in self.cross]
 
         kv, mem_face = self._fork_audio.run([body, face])
@@ -333,39 +387,41 @@ class EmageEngine:
     def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body):
         """One window of EmageAudioModel.forward (M.py:265-341) given the hoisted audio tensors.
         win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows)."""
-        bs, t, _ = win_in.shape
+        bs, t = (win_in.p.batch, win_in.p.rows) if isinstance(win_in, ops.Act) and win_in.f is None else _f32(win_in).shape[:2]
         E = self.E
         spk_f, spk_b = speaker_id_rows
-        hint = self.motion_encoder(win_in)                                              # M.py:271
+        ns = _ns()
+        hint = self.motion_encoder(win_in, want="p" if ns else "f")                    # M.py:271
 
         def face_branch():                                                              # M.py:288-294
-            hint_face = self.hint_face(hint)
-            mem_f = self.face_mem_hint(hint_face, residual=mem_face_audio)
-            x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
-            for layer in self.face_dec:
-                x = layer(x, layer.project_memory(mem_f))
-            rec = self.out_proj["face"](x)
-            return {"rec_face": rec, "cls_face": self.cls["face"](rec)}
+            hint_face = self.hint_face(hint, want="p" if ns else "f")
+            mem_f = self.face_mem_hint(hint_face, residual=mem_face_audio, want="p" if ns else "f")
+            x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E, nsplit=ns)
+            for i, layer in enumerate(self.face_dec):
+                x = layer(x, layer.project_memory(mem_f), want="fp" if i + 1 < len(self.face_dec) else "p")
+            rec = self.out_proj["face"](x, want="fp")
+            return {"rec_face": _f32(rec), "cls_face": self.cls["face"](rec)}
 
         def body_branch():                                                              # M.py:297-330
-            hint_body = self.hint_body(hint)
-            x = ops.add_rows(self.moton_proj(hint_body), self.pe, spk_b, ops.ROW_PE, ops.ROW_SPK, bs, t, E)
+            hint_body = self.hint_body(hint, want="p" if ns else "f")
+            x = ops.add_rows(self.moton_proj(hint_body), self.pe, spk_b, ops.ROW_PE, ops.ROW_SPK, bs, t, E, nsplit=ns)
             fea = self.self_enc(x)
-            fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E)
+            fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E, nsplit=ns)
             x = fea
-            for layer, kv in zip(self.cross, kv_body):
-                x = layer(x, kv)
-            fea = ops.add2(fea, x)
+            for i, (layer, kv) in enumerate(zip(self.cross, kv_body)):
+                x = layer(x, kv, want="fp" if i + 1 < len(self.cross) else "f")
+            fea = ops.add2(_f32(fea), _f32(x), nsplit=ns, f32=ns == 0)
             lat = {p: self.to_latent[p](fea) for p in PARTS[1:]}
             others = {"upper": ("hands", "lower"), "hands": ("upper", "lower"), "lower": ("upper", "hands")}
 
             def refine(p):
                 a, b = others[p]
                 layer = self.refine[p]
-                tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E)
-                r = layer(tgt, layer.project_memory(ops.add2(lat[a], lat[b])))
-                rec = self.out_proj[p](ops.add2(lat[p], r))
-                return {"rec_" + p: rec, "cls_" + p: self.cls[p](rec)}
+                tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E, nsplit=ns)
+                mem = ops.add2(lat[a], lat[b], nsplit=ns, f32=ns == 0)
+                r = layer(tgt, layer.project_memory(mem))
+                rec = self.out_proj[p](ops.add2(lat[p], r, nsplit=ns, f32=ns == 0), want="fp")
+                return {"rec_" + p: _f32(rec), "cls_" + p: self.cls[p](rec)}
 
             out = {}
             for d in self._fork_parts.run([lambda p=p: refine(p) for p in PARTS[1:]]):
@@ -408,7 +464,7 @@ class VQEngine:
         """EmageVQVAEConv.decode / decode_from_latent (M.py:56-70) -> (pose features, indices)."""
         if index is None:
             index = ops.l2_argmin(latent.contiguous(), self.codebook[p], self.e2[p])
-        return self.decoder[p](ops.gather_rows(self.codebook[p], index.contiguous())), index
+        return self.decoder[p](ops.gather_rows(self.codebook[p], index.contiguous(), nsplit=_ns())), index
 
     def decode(self, index, latent, get_global_motion=False, ref_trans=None):
         """index/latent: dicts part -> tensor or None.  Returns the reference's 4-key dict (M.py:193)."""
@@ -507,7 +563,7 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
     off = 0
     for wi, (s, e, keep) in enumerate(plan):
         t = e - s
-        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre)
+        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre, nsplit=_ns(), f32=_ns() == 0)
         mem_face, kv = hoisted[wi]
         out = engine.window(win_in, spk, mem_face, kv)
         for k in acc:

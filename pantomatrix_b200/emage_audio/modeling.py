@@ -392,7 +392,9 @@ class EmageAudioModel(_EngineOwner):
         mask = mask.to(device=dev, dtype=torch.float32).contiguous()
         bs, t, ch = motion.shape
         # no seed splice here: pre = 0 makes window_input the plain `where(mask==1, embedding, motion)`
-        win_in = ops.window_input(motion, mask, motion[:, :0].contiguous(), eng.mask_embedding, 0, t, 0)
+        ns = E._ns()
+        win_in = ops.window_input(motion, mask, motion[:, :0].contiguous(), eng.mask_embedding, 0, t, 0,
+                                  nsplit=ns, f32=ns == 0)
         mem_face, kv = eng.audio_phase(audio, 0, 0, 1, audio.shape[1], t)
         return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv)
 

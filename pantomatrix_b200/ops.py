@@ -99,52 +99,92 @@ def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, st
     return y1, sc
 
 
-def add_layernorm(x, r, gamma, beta, eps=1e-5, out=None):
+class Act:
+    """One activation as fp32 tensor (`f`) and/or split-bf16 planes (`p`); either may be None."""
+    __slots__ = ("f", "p")
+
+    def __init__(self, f=None, p=None):
+        self.f, self.p = f, p
+
+
+def _new_planes(nsplit, lead_shape, ch, device, slack_rows=0):
+    """Planes for an activation of shape (*lead_shape, ch); lead_shape = (batch, rows)."""
+    batch, rows = lead_shape
+    ld = _round_up(ch, 8)
+    if slack_rows:
+        buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=device, dtype=torch.bfloat16)
+        buf[:, batch * rows:].zero_()
+        t = buf[:, :batch * rows].view(nsplit, batch, rows, ld)
+    else:
+        t = torch.empty(nsplit, batch, rows, ld, device=device, dtype=torch.bfloat16)
+    return Planes(t, rows, ch, slack_rows)
+
+
+def _pargs(pl):
+    if pl is None:
+        return None, 0, 0, 0
+    return pl.t.data_ptr(), pl.t.stride(0), pl.t.stride(2), pl.t.shape[0]
+
+
+def _result(f, pl, nsplit):
+    return f if nsplit == 0 else Act(f, pl)
+
+
+def add_layernorm(x, r, gamma, beta, eps=1e-5, nsplit=0, f32=True):
     _chk(x)
     assert x.is_contiguous() and (r is None or (r.is_contiguous() and r.shape == x.shape))
     ch = x.shape[-1]
-    out = torch.empty_like(x) if out is None else out
-    _call("pm_add_layernorm_f32", x.data_ptr(), _ptr(r), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-          x.numel() // ch, ch, float(eps), _stream())
-    return out
+    rows = x.numel() // ch
+    out = torch.empty_like(x) if (f32 or not nsplit) else None
+    pl = _new_planes(nsplit, (x.shape[0], rows // x.shape[0]), ch, x.device) if nsplit else None
+    _call("pm_add_layernorm_f32", x.data_ptr(), _ptr(r), gamma.data_ptr(), beta.data_ptr(), _ptr(out),
+          rows, ch, float(eps), *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
-def attention(q, k, v, batch, heads, tq, tk, head_dim):
+def attention(q, k, v, batch, heads, tq, tk, head_dim, nsplit=0, f32=True):
     """q: (batch*tq, >=heads*head_dim) view, k/v: (batch*tk, ...) views (column slices allowed)."""
     for t in (q, k, v):
         _chk(t)
-    out = torch.empty(batch * tq, heads * head_dim, device=q.device, dtype=torch.float32)
+    E = heads * head_dim
+    out = torch.empty(batch * tq, E, device=q.device, dtype=torch.float32) if (f32 or not nsplit) else None
+    pl = _new_planes(nsplit, (batch, tq), E, q.device) if nsplit else None
     _call("pm_attention_f32", q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-          out.data_ptr(), out.stride(0), batch, heads, tq, tk, head_dim, _stream())
-    return out
+          _ptr(out), E, batch, heads, tq, tk, head_dim, *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
-def add_rows(x, pe, spk, first, second, batch, rows, ch):
-    out = torch.empty(batch, rows, ch, device=(pe if pe is not None else spk).device, dtype=torch.float32)
+def add_rows(x, pe, spk, first, second, batch, rows, ch, nsplit=0, f32=True):
+    dev = (pe if pe is not None else spk).device
+    out = torch.empty(batch, rows, ch, device=dev, dtype=torch.float32) if (f32 or not nsplit) else None
     if x is not None:
         _chk(x)
-        assert x.is_contiguous() and x.numel() == out.numel()
-    _call("pm_add_rows_f32", _ptr(x), _ptr(pe), _ptr(spk), first, second, out.data_ptr(), batch, rows, ch, _stream())
-    return out
+        assert x.is_contiguous() and x.numel() == batch * rows * ch
+    pl = _new_planes(nsplit, (batch, rows), ch, dev) if nsplit else None
+    _call("pm_add_rows_f32", _ptr(x), _ptr(pe), _ptr(spk), first, second, _ptr(out), batch, rows, ch, *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
-def add2(a, b):
+def add2(a, b, nsplit=0, f32=True):
     _chk(a), _chk(b)
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
-    out = torch.empty_like(a)
-    _call("pm_add2_f32", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
-    return out
+    out = torch.empty_like(a) if (f32 or not nsplit) else None
+    ch = a.shape[-1]
+    pl = _new_planes(nsplit, (a.shape[0], a.numel() // ch // a.shape[0]), ch, a.device) if nsplit else None
+    _call("pm_add2_f32", a.data_ptr(), b.data_ptr(), _ptr(out), a.numel(), ch, *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
-def window_input(motion, mask, seed, mask_embedding, start, win_len, pre):
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True):
     _chk(motion), _chk(mask), _chk(seed)
     assert motion.is_contiguous() and mask.is_contiguous() and seed.is_contiguous()
     batch, total_len, ch = motion.shape
     assert mask.shape == motion.shape and seed.shape == (batch, pre, ch)
-    out = torch.empty(batch, win_len, ch, device=motion.device, dtype=torch.float32)
+    out = torch.empty(batch, win_len, ch, device=motion.device, dtype=torch.float32) if (f32 or not nsplit) else None
+    pl = _new_planes(nsplit, (batch, win_len), ch, motion.device) if nsplit else None
     _call("pm_window_input_f32", motion.data_ptr(), mask.data_ptr(), seed.data_ptr(), mask_embedding.data_ptr(),
-          out.data_ptr(), batch, total_len, start, win_len, pre, ch, _stream())
-    return out
+          _ptr(out), batch, total_len, start, win_len, pre, ch, *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
 def l2_argmin(z, codebook, e2):
@@ -166,13 +206,17 @@ def row_argmax(x):
     return idx
 
 
-def gather_rows(codebook, index):
+def gather_rows(codebook, index, nsplit=0, f32=True):
     _chk(codebook), _chk(index, torch.int64)
     assert index.is_contiguous()
-    out = torch.empty(*index.shape, codebook.shape[1], device=codebook.device, dtype=torch.float32)
-    _call("pm_gather_rows_f32", codebook.data_ptr(), index.data_ptr(), index.numel(), codebook.shape[1],
-          out.data_ptr(), _stream())
-    return out
+    ch = codebook.shape[1]
+    out = torch.empty(*index.shape, ch, device=codebook.device, dtype=torch.float32) if (f32 or not nsplit) else None
+    pl = None
+    if nsplit:
+        lead = (index.shape[0], index.numel() // index.shape[0]) if index.dim() > 1 else (1, index.numel())
+        pl = _new_planes(nsplit, lead, ch, codebook.device)
+    _call("pm_gather_rows_f32", codebook.data_ptr(), index.data_ptr(), index.numel(), ch, _ptr(out), *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
 
 
 def row_sqnorm(x):
@@ -218,10 +262,17 @@ def _round_up(x, m):
 class Planes:
     """`nsplit` bf16 planes of a (batch, rows, ch) activation: tensor (nsplit, batch, rows_alloc, ld) bf16
     with x ~ sum_p planes[p].  Only [:, :, :rows, :ch] is meaningful."""
-    __slots__ = ("t", "rows", "ch")
+    __slots__ = ("t", "rows", "ch", "slack")
 
-    def __init__(self, t, rows, ch):
-        self.t, self.rows, self.ch = t, rows, ch
+    def __init__(self, t, rows, ch, slack=0):
+        self.t, self.rows, self.ch, self.slack = t, rows, ch, slack   # slack: zeroed rows after the last clip
+
+    def flat(self):
+        """(nsplit, 1, batch*rows, ld) view: all clips as one tall matrix (needs clip-contiguous rows)."""
+        ns, b, r, ld = self.t.shape
+        assert self.t.stride(1) == r * self.t.stride(2)
+        return Planes(self.t.as_strided((ns, 1, b * r, ld), (self.t.stride(0), b * r * self.t.stride(2), self.t.stride(2), 1),
+                                        self.t.storage_offset()), b * r, self.ch, self.slack)
 
     @property
     def nsplit(self):
@@ -237,18 +288,11 @@ def split_bf16(x, nsplit, slack_rows=0):
     appended after the last clip for strided-view consumers."""
     _chk(x)
     batch, rows, ch = x.shape
-    ld = _round_up(ch, 8)
-    if slack_rows:
-        buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=x.device, dtype=torch.bfloat16)
-        buf[:, batch * rows:].zero_()
-        t = buf[:, :batch * rows].view(nsplit, batch, rows, ld)
-        ps = buf.stride(0)
-    else:
-        t = torch.empty(nsplit, batch, rows, ld, device=x.device, dtype=torch.bfloat16)
-        ps = t.stride(0)
+    pl = _new_planes(nsplit, (batch, rows), ch, x.device, slack_rows)
     x_bs, ldx = _bs_ld(x)
-    _call("pm_split_bf16", x.data_ptr(), x_bs, ldx, batch, rows, ch, t.data_ptr(), ps, rows * ld, ld, nsplit, _stream())
-    return Planes(t, rows, ch)
+    _call("pm_split_bf16", x.data_ptr(), x_bs, ldx, batch, rows, ch, pl.t.data_ptr(), pl.t.stride(0), pl.t.stride(1),
+          pl.t.stride(2), nsplit, _stream())
+    return pl
 
 
 class PackedW:
@@ -272,7 +316,7 @@ class PackedW:
 
 
 def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0,
-               residual=None, want_f32=True, out_nsplit=0, out=None, a_view=None):
+               residual=None, want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0):
     """Tensor-core tap-GEMM.  `a_view` = (rows_in, cin, lda) overrides the logical view of the A planes
     (strided convs pass the (rows/s, s*C) view of the same memory).  Returns (fp32 out | None, Planes | None)."""
     t = a.t
@@ -291,8 +335,7 @@ def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, ac
     o_bs, ldo = _bs_ld(out_f) if out_f is not None else (0, 0)
     out_p = None
     if out_nsplit:
-        ldob = _round_up(cout, 8)
-        out_p = Planes(torch.empty(out_nsplit, batch, rows_out, ldob, device=dev, dtype=torch.bfloat16), rows_out, cout)
+        out_p = _new_planes(out_nsplit, (batch, rows_out), cout, dev, out_slack)
     r_bs, ldr = _bs_ld(residual) if residual is not None else (0, 0)
     if residual is not None:
         _chk(residual)

@@ -11,6 +11,35 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
 launch_count = 0
 
+from pantomatrix_b200.ops import Act, PackedW, Planes, _round_up  # noqa: E402,F401  (same containers as the product)
+
+
+def _split(v, nsplit):
+    planes, rem = [], v
+    for _ in range(nsplit):
+        p = rem.to(torch.bfloat16)
+        planes.append(p)
+        rem = rem - p.float()
+    return planes
+
+
+def _mk_planes(y, nsplit, slack_rows=0):
+    """(batch, rows, ch) fp32 -> Planes with NaN-poisoned padding (catches reads of uninitialised memory)."""
+    batch, rows, ch = y.shape
+    ld = _round_up(ch, 8)
+    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=torch.bfloat16)
+    buf[:, batch * rows:] = 0
+    for i, p in enumerate(_split(y.reshape(batch * rows, ch).float(), nsplit)):
+        buf[i, :batch * rows, :ch] = p
+    return Planes(buf[:, :batch * rows].view(nsplit, batch, rows, ld), rows, ch, slack_rows)
+
+
+def _res(y, nsplit, f32, lead=None):
+    if nsplit == 0:
+        return y
+    y3 = y if lead is None else y.reshape(*lead, y.shape[-1])
+    return Act(y if f32 else None, _mk_planes(y3, nsplit))
+
 
 def _act(v, act, slope):
     return F.relu(v) if act == ACT_RELU else F.leaky_relu(v, slope) if act == ACT_LEAKY else v
@@ -39,39 +68,39 @@ def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, st
     return y1.contiguous(), sc.contiguous()
 
 
-def add_layernorm(x, r, gamma, beta, eps=1e-5, out=None):
-    return F.layer_norm(x if r is None else x + r, (x.shape[-1],), gamma, beta, eps)
+def add_layernorm(x, r, gamma, beta, eps=1e-5, nsplit=0, f32=True):
+    return _res(F.layer_norm(x if r is None else x + r, (x.shape[-1],), gamma, beta, eps), nsplit, f32)
 
 
-def attention(q, k, v, batch, heads, tq, tk, head_dim):
+def attention(q, k, v, batch, heads, tq, tk, head_dim, nsplit=0, f32=True):
     E = heads * head_dim
     qq = q[:, :E].reshape(batch, tq, heads, head_dim).transpose(1, 2)
     kk = k[:, :E].reshape(batch, tk, heads, head_dim).transpose(1, 2)
     vv = v[:, :E].reshape(batch, tk, heads, head_dim).transpose(1, 2)
     att = torch.softmax(qq @ kk.transpose(-1, -2) / head_dim ** 0.5, -1)
-    return (att @ vv).transpose(1, 2).reshape(batch * tq, E)
+    return _res((att @ vv).transpose(1, 2).reshape(batch * tq, E), nsplit, f32, lead=(batch, tq))
 
 
-def add_rows(x, pe, spk, first, second, batch, rows, ch):
+def add_rows(x, pe, spk, first, second, batch, rows, ch, nsplit=0, f32=True):
     v = torch.zeros(batch, rows, ch) if x is None else x.reshape(batch, rows, ch)
     for code in (first, second):
         if code == ROW_PE:
             v = v + pe[None, :rows]
         elif code == ROW_SPK:
             v = v + spk[:, None]
-    return v.contiguous()
+    return _res(v.contiguous(), nsplit, f32)
 
 
-def add2(a, b):
-    return a + b
+def add2(a, b, nsplit=0, f32=True):
+    return _res(a + b, nsplit, f32)
 
 
-def window_input(motion, mask, seed, mask_embedding, start, win_len, pre):
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True):
     wm, wk = motion[:, start:start + win_len].clone(), mask[:, start:start + win_len].clone()
     if pre:
         wm[:, :pre] = torch.where(wk[:, :pre] == 0, motion[:, start:start + pre], seed)
         wk[:, :pre] = 0
-    return torch.where(wk == 1, mask_embedding.view(1, 1, -1).expand_as(wm), wm)
+    return _res(torch.where(wk == 1, mask_embedding.view(1, 1, -1).expand_as(wm), wm), nsplit, f32)
 
 
 def l2_argmin(z, codebook, e2):
@@ -84,8 +113,9 @@ def row_argmax(x):
     return x.argmax(-1)
 
 
-def gather_rows(codebook, index):
-    return codebook[index]
+def gather_rows(codebook, index, nsplit=0, f32=True):
+    y = codebook[index]
+    return _res(y, nsplit, f32, lead=(index.shape[0], index.numel() // index.shape[0]) if index.dim() > 1 else (1, index.numel()))
 
 
 def row_sqnorm(x):
@@ -119,30 +149,14 @@ def global_trans(rec, ref_trans, dt, vel_off=54):
 
 
 # ---- tensor-core engine stand-ins (same Planes / PackedW containers as the product) --------------------
-from pantomatrix_b200.ops import PackedW, Planes, _round_up  # noqa: E402,F401
-
-
-def _split(v, nsplit):
-    planes, rem = [], v
-    for _ in range(nsplit):
-        p = rem.to(torch.bfloat16)
-        planes.append(p)
-        rem = rem - p.float()
-    return planes
 
 
 def split_bf16(x, nsplit, slack_rows=0):
-    batch, rows, ch = x.shape
-    ld = _round_up(ch, 8)
-    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=torch.bfloat16)
-    buf[:, batch * rows:] = 0
-    for i, p in enumerate(_split(x.reshape(batch * rows, ch).float(), nsplit)):
-        buf[i, :batch * rows, :ch] = p
-    return Planes(buf[:, :batch * rows].view(nsplit, batch, rows, ld), rows, ch)
+    return _mk_planes(x, nsplit, slack_rows)
 
 
 def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0, residual=None,
-               want_f32=True, out_nsplit=0, out=None, a_view=None):
+               want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0):
     t = a.t
     nsplit, batch = t.shape[0], t.shape[1]
     rows_a, cin, lda = (a.rows, a.ch, t.stride(2)) if a_view is None else a_view
@@ -165,13 +179,7 @@ def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_c
         cols = w.cout if act_cols <= 0 else act_cols
         y = torch.cat([_act(y[..., :cols], act, slope), y[..., cols:]], -1)
     assert torch.isfinite(y).all(), "read uninitialised plane memory"
-    out_p = None
-    if out_nsplit:
-        ld = _round_up(w.cout, 8)
-        tt = torch.zeros(out_nsplit, batch, rows_out, ld, dtype=torch.bfloat16)
-        for i, p in enumerate(_split(y, out_nsplit)):
-            tt[i, :, :, :w.cout] = p
-        out_p = Planes(tt, rows_out, w.cout)
+    out_p = _mk_planes(y, out_nsplit, out_slack) if out_nsplit else None
     if want_f32:
         if out is not None:
             out.copy_(y)

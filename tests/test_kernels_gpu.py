@@ -241,3 +241,40 @@ def test_global_trans_sequential_sum(ops):
         z.append(v[:, i - 1, 2:3] * (1 / 30) + z[-1])
     assert torch.equal(got[:, :, 0], torch.cat(x, 1)) and torch.equal(got[:, :, 2], torch.cat(z, 1))
     assert torch.equal(got[:, :, 1], v[:, :, 1])
+
+
+def _planes_value(pl):
+    return pl.t[:, :, :, :pl.ch].float().sum(0)
+
+
+@pytest.mark.parametrize("nsplit", [1, 2, 3])
+def test_fused_plane_outputs(ops, nsplit):
+    """Producers that write their result directly as split-bf16 planes (the A-operand format of the tensor-core
+    GEMM): planes must re-assemble the fp32 result to 2^-8 / 2^-16 / 2^-24 relative accuracy."""
+    tol = 2.0 ** (-8 * nsplit) * 1.01
+    E = 768
+    x, r, g, b = _rand(4, 60, E, seed=50), _rand(4, 60, E, seed=51), _rand(E, seed=52), _rand(E, seed=53)
+    ref = ops.add_layernorm(x, r, g, b)
+    got = ops.add_layernorm(x, r, g, b, nsplit=nsplit)
+    assert torch.equal(got.f, ref) and (_planes_value(got.p) - ref).abs().max() <= tol * ref.abs().max()
+    only = ops.add_layernorm(x, r, g, b, nsplit=nsplit, f32=False)
+    assert only.f is None and torch.equal(only.p.t[..., :E], got.p.t[..., :E])
+    qkv = _rand(4 * 60, 3 * E, seed=54)
+    ref = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], 4, 4, 60, 60, 192)
+    got = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], 4, 4, 60, 60, 192, nsplit=nsplit, f32=False)
+    assert got.f is None and (_planes_value(got.p).reshape(240, E) - ref).abs().max() <= tol * ref.abs().max()
+    pe, spk = _rand(128, E, seed=55), _rand(4, E, seed=56)
+    ref = ops.add_rows(x, pe, spk, ops.ROW_SPK, ops.ROW_PE, 4, 60, E)
+    got = ops.add_rows(x, pe, spk, ops.ROW_SPK, ops.ROW_PE, 4, 60, E, nsplit=nsplit)
+    assert torch.equal(got.f, ref) and (_planes_value(got.p) - ref).abs().max() <= tol * ref.abs().max()
+    got = ops.add2(x, r, nsplit=nsplit, f32=False)
+    assert (_planes_value(got.p) - (x + r)).abs().max() <= tol * (x + r).abs().max()
+    cb = _rand(256, 256, seed=57)
+    idx = torch.randint(0, 256, (4, 33), generator=torch.Generator().manual_seed(58)).cuda()
+    got = ops.gather_rows(cb, idx, nsplit=nsplit)
+    assert torch.equal(got.f, cb[idx]) and (_planes_value(got.p) - cb[idx]).abs().max() <= tol * cb.abs().max()
+    motion, seed, emb = _rand(3, 130, 337, seed=59), _rand(3, 4, 337, seed=60), _rand(337, seed=61)
+    mask = (torch.rand(3, 130, 337, generator=torch.Generator().manual_seed(62)) > 0.5).float().cuda()
+    ref = ops.window_input(motion, mask, seed, emb, 60, 64, 4)
+    got = ops.window_input(motion, mask, seed, emb, 60, 64, 4, nsplit=nsplit, f32=False)
+    assert got.p.t.shape[-1] == 344 and (_planes_value(got.p) - ref).abs().max() <= tol * ref.abs().max()
