@@ -49,7 +49,7 @@ def wav_out_len(n: int) -> int:
 # Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores
 # with plain bf16 / bf16x3 / bf16x6 split operands (see csrc/pm_tapgemm_tc.cu).
 PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3}
-_STATE = {"nsplit": PRECISIONS["fp32"]}
+_STATE = {"nsplit": PRECISIONS["fp32"], "fork": True}      # fork: overlap independent branches on side streams
 
 
 def set_precision(name: str) -> None:
@@ -84,7 +84,7 @@ class _Fork:
         self.n_side, self.streams = n_side, None
 
     def run(self, fns):
-        if not torch.cuda.is_available() or len(fns) == 1:
+        if not torch.cuda.is_available() or len(fns) == 1 or not _STATE["fork"]:
             return [fn() for fn in fns]
         if self.streams is None:
             self.streams = [torch.cuda.Stream() for _ in range(self.n_side)]
