@@ -103,18 +103,29 @@ __global__ void __launch_bounds__(NT) attention_f32_kernel(
         for (int a = 0; a < 4; ++a) acc[a][m] = fmaf(pv[a], vv, acc[a][m]);
       }
     }
+    // stage the 64 x 192 output tile in smem (the Q region is dead by now) so global writes are row-contiguous
+    __syncthreads();
+    float* Os = Qs;                      // [TMAX][HD]
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int r = tr * 4 + a;
-      if (r >= tq) continue;
-      if (O) {
-        float* o = O + (long long)(b * tq + r) * ldo + h * HD;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int m = 0; m < 12; ++m) o[tc + 16 * m] = acc[a][m];
-      }
+      for (int m = 0; m < 12; ++m) Os[(tr * 4 + a) * HD + tc + 16 * m] = acc[a][m];
+  }
+  __syncthreads();
+  {
+    const float* Os = Qs;
+    const bool vec_p = P.ptr && ((P.ld & 3) == 0) && ((P.ps & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.ptr) & 7) == 0);
+    for (int i = tid; i < tq * (HD / 4); i += NT) {
+      const int r = i / (HD / 4), c4 = i % (HD / 4);
+      const float4 v = *reinterpret_cast<const float4*>(Os + r * HD + c4 * 4);
+      const long long row = (long long)b * tq + r;
+      if (O) *reinterpret_cast<float4*>(O + row * ldo + h * HD + c4 * 4) = v;
       if (P.ptr) {
-#pragma unroll
-        for (int m = 0; m < 12; ++m) pm_store_planes(P, (long long)b * tq + r, h * HD + tc + 16 * m, acc[a][m]);
+        if (vec_p) pm_store_planes4(P, row, h * HD + c4 * 4, v);
+        else {
+          pm_store_planes(P, row, h * HD + c4 * 4, v.x); pm_store_planes(P, row, h * HD + c4 * 4 + 1, v.y);
+          pm_store_planes(P, row, h * HD + c4 * 4 + 2, v.z); pm_store_planes(P, row, h * HD + c4 * 4 + 3, v.w);
+        }
       }
     }
   }
@@ -131,7 +142,7 @@ extern "C" int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, heads * head_dim, false));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (head_dim != HD || tq > TMAX || tk > TMAX || tq <= 0 || tk <= 0) return PM_EUNSUPPORTED;
-  PM_REQUIRE((ldq & 3) == 0 && (ldk & 3) == 0 && (ldv & 3) == 0);
+  PM_REQUIRE((ldq & 3) == 0 && (ldk & 3) == 0 && (ldv & 3) == 0 && (!O || (ldo & 3) == 0));
   if (batch == 0) return PM_OK;
   static bool configured = false;
   if (!configured) {

@@ -58,21 +58,27 @@ __device__ __forceinline__ void pm_split3(float v, __nv_bfloat16 (&p)[3]) {
   p[2] = __float2bfloat16_rn(r);
 }
 
+// Successive planes are peeled off a running remainder: no dynamically indexed temporaries (they would live in
+// local memory).
 __device__ __forceinline__ void pm_store_planes(const PmPlanes& P, long long row, int c, float v) {
-  __nv_bfloat16 pp[3];
-  pm_split3(v, pp);
   __nv_bfloat16* o = P.ptr + row * P.ld + c;
-  for (int pl = 0; pl < P.nsplit; ++pl) o[(long long)pl * P.ps] = pp[pl];
+  for (int pl = 0; pl < P.nsplit; ++pl) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    o[(long long)pl * P.ps] = h;
+    v -= __bfloat162float(h);
+  }
 }
 
 // 4 consecutive channels, c % 4 == 0, ld % 4 == 0, ps % 4 == 0, 8-byte aligned base
 __device__ __forceinline__ void pm_store_planes4(const PmPlanes& P, long long row, int c, float4 v) {
-  __nv_bfloat16 a[3], b[3], cc[3], d[3];
-  pm_split3(v.x, a); pm_split3(v.y, b); pm_split3(v.z, cc); pm_split3(v.w, d);
   __nv_bfloat16* o = P.ptr + row * P.ld + c;
   for (int pl = 0; pl < P.nsplit; ++pl) {
-    __align__(8) __nv_bfloat16 h[4] = {a[pl], b[pl], cc[pl], d[pl]};
-    *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = *reinterpret_cast<const uint2*>(h);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t*>(&lo);
+    w.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = w;
+    v.x -= __low2float(lo); v.y -= __high2float(lo); v.z -= __low2float(hi); v.w -= __high2float(hi);
   }
 }
 

@@ -16,6 +16,7 @@
 //                            and/or bf16 split planes for the next GEMM
 // Contract and reference call sites: include/pm_emage.h (pm_tapgemm_tc).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
@@ -273,21 +274,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         }
       }
       if (ob) {
+        // planes peeled off a running remainder (static register indexing only)
         for (int pl = 0; pl < p.out_nsplit; ++pl) {
           __nv_bfloat16* dst = ob + (long long)pl * p.ob_ps + n;
-          __align__(16) __nv_bfloat16 h[32];
+          uint32_t h[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            __nv_bfloat16 pp[3];
-            pm_split3(v[j], pp);
-            h[j] = pp[pl];
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            h[j] = *reinterpret_cast<const uint32_t*>(&t);
+            v[2 * j] -= __low2float(t);
+            v[2 * j + 1] -= __high2float(t);
           }
           if (vec_b && full) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(h)[j];
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (n + j < p.cout) dst[j] = h[j];
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.cout) dst[j] = __ushort_as_bfloat16((unsigned short)((h[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu));
           }
         }
       }
@@ -320,22 +324,15 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const int r = (int)(i / ch4), c4 = (int)(i - (long long)r * ch4);
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * ldx + 4 * c4);
-      __nv_bfloat16 a[3], bq[3], c[3], d[3];
-      pm_split3(v.x, a); pm_split3(v.y, bq); pm_split3(v.z, c); pm_split3(v.w, d);
-      __nv_bfloat16* o = ob + (long long)r * ldo + 4 * c4;
-      for (int pl = 0; pl < nsplit; ++pl) {
-        __align__(8) __nv_bfloat16 h[4] = {a[pl], bq[pl], c[pl], d[pl]};
-        *reinterpret_cast<uint2*>(o + (long long)pl * o_ps) = *reinterpret_cast<const uint2*>(h);
-      }
+      const PmPlanes P{ob, o_ps, ldo, nsplit};
+      pm_store_planes4(P, r, 4 * c4, v);
     }
   } else {
     const long long total = (long long)rows * ch;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const int r = (int)(i / ch), c = (int)(i - (long long)r * ch);
-      __nv_bfloat16 pp[3];
-      pm_split3(xb[(long long)r * ldx + c], pp);
-      __nv_bfloat16* o = ob + (long long)r * ldo + c;
-      for (int pl = 0; pl < nsplit; ++pl) o[(long long)pl * o_ps] = pp[pl];
+      const PmPlanes P{ob, o_ps, ldo, nsplit};
+      pm_store_planes(P, r, c, xb[(long long)r * ldx + c]);
     }
   }
 }
@@ -370,7 +367,8 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
 template <int BN>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
-  int stages = (200 * 1024) / stage_bytes;
+  static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
+  int stages = (env_kb * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return PM_EUNSUPPORTED;
   p.stages = stages;
@@ -413,7 +411,10 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   const int NB = 128 / R;
   // N tile: 128 columns unless that leaves most of the 148 SMs idle (the M = 2048 transformer GEMMs), then 64
   int BNsel = cout <= 64 ? 64 : 128;
-  if (BNsel == 128 && (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB) * pm_cdiv(cout, 128) < 120) BNsel = 64;
+  static const int env_bn = getenv("PM_TC_BN") ? atoi(getenv("PM_TC_BN")) : 0;      // tuning override: 64 | 128
+  if (BNsel == 128 && env_bn == 64) BNsel = 64;
+  else if (BNsel == 128 && env_bn == 0 &&
+           (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB) * pm_cdiv(cout, 128) < 120) BNsel = 64;
   PM_REQUIRE(w_rows % BNsel == 0);
 
   TcParams p;
