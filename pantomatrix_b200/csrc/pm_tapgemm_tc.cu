@@ -412,9 +412,7 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   // N tile: 128 columns unless that leaves most of the 148 SMs idle (the M = 2048 transformer GEMMs), then 64
   int BNsel = cout <= 64 ? 64 : 128;
   static const int env_bn = getenv("PM_TC_BN") ? atoi(getenv("PM_TC_BN")) : 0;      // tuning override: 64 | 128
-  if (BNsel == 128 && env_bn == 64) BNsel = 64;
-  else if (BNsel == 128 && env_bn == 0 &&
-           (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB) * pm_cdiv(cout, 128) < 120) BNsel = 64;
+  if (BNsel == 128 && env_bn == 64) BNsel = 64;   // measured slower (profiles/gemm_microbench_r1.md): off by default
   PM_REQUIRE(w_rows % BNsel == 0);
 
   TcParams p;

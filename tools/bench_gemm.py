@@ -1,4 +1,4 @@
-"""Microbenchmark of pm_tapgemm_tc on the EMAGE shapes (warm L2, CUDA events, 30 reps after 5 warm-ups).
+"""Microbenchmark of pm_tapgemm_tc on the EMAGE shapes (warm L2, CUDA events around CUDA-graph replays).
     [PM_TC_BN=64|128] [PM_TC_SMEM_KB=...] python tools/bench_gemm.py"""
 import math
 import os
@@ -45,16 +45,24 @@ def main():
             pw = ops.PackedW(w, ns)
             for out_mode in ("f32", "f+p"):
                 kw = dict(rows_out=rows_out, pad=pad, act=ops.ACT_RELU, out_nsplit=ns if out_mode == "f+p" else 0)
-                for _ in range(5):
+                out = torch.empty(b, rows_out, cout, device="cuda")
+                kw["out"] = out
+                for _ in range(3):
                     ops.tapgemm_tc(a, pw, bias, **kw)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()          # 20 back-to-back launches replayed as a graph: GPU time,
+                with torch.cuda.graph(graph):           # not Python / ctypes / descriptor-encode time
+                    for _ in range(20):
+                        ops.tapgemm_tc(a, pw, bias, **kw)
+                graph.replay()
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 s.record()
-                for _ in range(30):
-                    ops.tapgemm_tc(a, pw, bias, **kw)
+                for _ in range(3):
+                    graph.replay()
                 e.record()
                 torch.cuda.synchronize()
-                us = s.elapsed_time(e) / 30 * 1e3
+                us = s.elapsed_time(e) / 60 * 1e3
                 fl = 2.0 * b * rows_out * cout * cin * taps
                 mult = {1: 1, 2: 3, 3: 6}[ns]
                 print(f"{name:34s} {ns:2d} {out_mode:>4s} {us:9.1f} {fl / us / 1e6:13.1f} {fl * mult / us / 1e6:10.1f}")
