@@ -41,6 +41,7 @@ struct TcParams {
   float* out_f32; long long o_bs; int ldo;
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
+  int dbg;   // tuning experiments only (PM_TC_DBG): 1 = no global stores, 2 = no epilogue, 4 = no TMA / MMA
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   const int l0 = blockIdx.x * p.R;
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
-  const int n_iter = p.taps * p.kblocks;
+  const int n_iter = (p.dbg & 4) ? 0 : p.taps * p.kblocks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -203,26 +204,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         }
         tc_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
       }
-      tc_commit(smem_u32(acc_bar));                      // accumulator complete
+      if (n_iter > 0) tc_commit(smem_u32(acc_bar));      // accumulator complete
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Storing that directly makes every
+    // warp store touch 32 different lines (measured: 12.5 us of a 16 us GEMM, profiles/gemm_microbench_r1.md), so the
+    // 32x32 chunk is transposed through shared memory (the operand ring is idle by now) and written with each
+    // quarter-warp covering one contiguous 128-byte row segment.
     const int q = warp & 3;
-    const int r = q * 32 + lane;                         // tile row == TMEM lane
-    const int b = b0 + r / p.R;
-    const int l = l0 + r % p.R;
-    const bool row_ok = b < p.batch && l < p.rows_out;
-    mbar_wait(smem_u32(acc_bar), 0);
+    if (!(p.dbg & 4)) mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
-    float* of = p.out_f32 ? p.out_f32 + (long long)b * p.o_bs + (long long)l * p.ldo : nullptr;
-    const float* rs = p.residual ? p.residual + (long long)b * p.r_bs + (long long)l * p.ldr : nullptr;
-    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)b * p.ob_bs + (long long)l * p.ldob : nullptr;
-    const bool vec_f = of && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
-    const bool vec_r = rs && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
-    const bool vec_b = ob && ((p.ldob & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 15) == 0) &&
-                       ((p.ob_bs & 7) == 0) && ((p.ob_ps & 7) == 0);
+    constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
+    float* stage = reinterpret_cast<float*>(tiles) + q * 32 * ST;  // 4.6 KB per warp
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;              // this lane's row-in-group / first column of its float4
+    const int r_shift = 31 - __clz(p.R);                           // R is a power of two
+    const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
+    const bool vec_r = p.residual && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
+    const bool vec_b = p.out_bf16 && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0) &&
+                       ((p.ob_bs & 3) == 0) && ((p.ob_ps & 3) == 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < ((p.dbg & 6) ? 0 : BN); c0 += 32) {
       uint32_t acc[32];
       float v[32];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -240,62 +242,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
       }
-      const int n = n0 + c0;
-      if (row_ok && n < p.cout) {
-      const bool full = n + 32 <= p.cout;
+      const int nb = n0 + c0;                                                      // first column of this chunk
+      if (nb >= p.cout || (p.dbg & 1)) continue;                                   // warp-uniform
+      // transpose: thread = row -> smem[row][0..31]
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stage + lane * ST + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const int n = nb + c4;                                                       // this lane's first column
+      const bool full4 = n + 4 <= p.cout;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (full || n + j < p.cout) v[j] += __ldg(p.bias + n + j);
-      }
-      if (rs) {
-        if (vec_r && full) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = *reinterpret_cast<const float4*>(rs + n + 4 * j);
-            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (n + j < p.cout) v[j] += rs[n + j];
+        if (full4) bias4 = make_float4(__ldg(p.bias + n), __ldg(p.bias + n + 1), __ldg(p.bias + n + 2), __ldg(p.bias + n + 3));
+        else {
+          if (n < p.cout) bias4.x = __ldg(p.bias + n);
+          if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
+          if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
         }
       }
-      if (p.act != PM_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (n + j < p.act_cols) v[j] = pm_act(v[j], p.act, p.slope);
-      }
-      if (of) {
-        if (vec_f && full) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(of + n + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (n + j < p.cout) of[n + j] = v[j];
-        }
-      }
-      if (ob) {
-        // planes peeled off a running remainder (static register indexing only)
-        for (int pl = 0; pl < p.out_nsplit; ++pl) {
-          __nv_bfloat16* dst = ob + (long long)pl * p.ob_ps + n;
-          uint32_t h[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            h[j] = *reinterpret_cast<const uint32_t*>(&t);
-            v[2 * j] -= __low2float(t);
-            v[2 * j + 1] -= __high2float(t);
-          }
-          if (vec_b && full) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int rt = q * 32 + 4 * i + sub_r;                                     // tile row
+        const int b = b0 + (rt >> r_shift);
+        const int l = l0 + (rt & (p.R - 1));
+        if (b >= p.batch || l >= p.rows_out || n >= p.cout) continue;
+        float4 x = *reinterpret_cast<const float4*>(stage + (4 * i + sub_r) * ST + c4);
+        x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+        if (p.residual) {
+          const float* rs = p.residual + (long long)b * p.r_bs + (long long)l * p.ldr + n;
+          if (vec_r && full4) {
+            const float4 t = *reinterpret_cast<const float4*>(rs);
+            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.cout) dst[j] = __ushort_as_bfloat16((unsigned short)((h[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu));
+            x.x += rs[0];
+            if (n + 1 < p.cout) x.y += rs[1];
+            if (n + 2 < p.cout) x.z += rs[2];
+            if (n + 3 < p.cout) x.w += rs[3];
+          }
+        }
+        if (p.act != PM_ACT_NONE) {
+          if (n < p.act_cols) x.x = pm_act(x.x, p.act, p.slope);
+          if (n + 1 < p.act_cols) x.y = pm_act(x.y, p.act, p.slope);
+          if (n + 2 < p.act_cols) x.z = pm_act(x.z, p.act, p.slope);
+          if (n + 3 < p.act_cols) x.w = pm_act(x.w, p.act, p.slope);
+        }
+        if (p.out_f32) {
+          float* of = p.out_f32 + (long long)b * p.o_bs + (long long)l * p.ldo + n;
+          if (vec_f && full4) *reinterpret_cast<float4*>(of) = x;
+          else {
+            of[0] = x.x;
+            if (n + 1 < p.cout) of[1] = x.y;
+            if (n + 2 < p.cout) of[2] = x.z;
+            if (n + 3 < p.cout) of[3] = x.w;
+          }
+        }
+        if (p.out_bf16) {
+          const PmPlanes P{p.out_bf16 + (long long)b * p.ob_bs, p.ob_ps, p.ldob, p.out_nsplit};
+          if (vec_b && full4) pm_store_planes4(P, l, n, x);
+          else {
+            pm_store_planes(P, l, n, x.x);
+            if (n + 1 < p.cout) pm_store_planes(P, l, n + 1, x.y);
+            if (n + 2 < p.cout) pm_store_planes(P, l, n + 2, x.z);
+            if (n + 3 < p.cout) pm_store_planes(P, l, n + 3, x.w);
           }
         }
       }
-      }  // row_ok
     }
   }
 
@@ -424,6 +435,8 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ob_ps = ob_ps; p.ob_bs = ob_bs; p.ldob = ldob;
   p.out_nsplit = out_bf16 ? out_nsplit : 0;
   p.stages = 0;
+  static const int env_dbg = getenv("PM_TC_DBG") ? atoi(getenv("PM_TC_DBG")) : 0;
+  p.dbg = env_dbg;
 
   CUtensorMap ma, mw;
   {
