@@ -79,6 +79,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     if (!(p.dbg & 4)) mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
     constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
-    float* stage = reinterpret_cast<float*>(tiles) + q * 32 * ST;  // 4.6 KB per warp
+    const uint32_t stage = smem_u32(tiles) + q * 32 * ST * 4;      // 4.6 KB per warp (shared-space address)
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;              // this lane's row-in-group / first column of its float4
     const int r_shift = 31 - __clz(p.R);                           // R is a power of two
     const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
@@ -244,10 +252,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       }
       const int nb = n0 + c0;                                                      // first column of this chunk
       if (nb >= p.cout || (p.dbg & 1)) continue;                                   // warp-uniform
+      if (p.dbg & 16) {                                                            // experiment: row-per-thread raw stores
+        const int rt = q * 32 + lane;
+        float* of = p.out_f32 + (long long)(b0 + (rt >> r_shift)) * p.o_bs + (long long)(l0 + (rt & (p.R - 1))) * p.ldo + nb;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(of + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        continue;
+      }
       // transpose: thread = row -> smem[row][0..31]
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stage + lane * ST + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int n = nb + c4;                                                       // this lane's first column
       const bool full4 = n + 4 <= p.cout;
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         const int b = b0 + (rt >> r_shift);
         const int l = l0 + (rt & (p.R - 1));
         if (b >= p.batch || l >= p.rows_out || n >= p.cout) continue;
-        float4 x = *reinterpret_cast<const float4*>(stage + (4 * i + sub_r) * ST + c4);
+        float4 x = lds128(stage + ((4 * i + sub_r) * ST + c4) * 4);
         x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
         if (p.residual) {
           const float* rs = p.residual + (long long)b * p.r_bs + (long long)l * p.ldr + n;
@@ -288,7 +302,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         }
         if (p.out_f32) {
           float* of = p.out_f32 + (long long)b * p.o_bs + (long long)l * p.ldo + n;
-          if (vec_f && full4) *reinterpret_cast<float4*>(of) = x;
+          if (p.dbg & 8) {                                   // experiment: everything but the store itself
+            if (x.x == 1.2345e38f) *reinterpret_cast<float4*>(of) = x;
+          } else if (vec_f && full4) *reinterpret_cast<float4*>(of) = x;
           else {
             of[0] = x.x;
             if (n + 1 < p.cout) of[1] = x.y;
