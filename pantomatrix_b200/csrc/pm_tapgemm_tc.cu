@@ -6,14 +6,14 @@
 // (p0*p0 + p0*p1 + p1*p0), 3 = bf16x6 (every product down to 2^-24): all products accumulate in one fp32
 // TMEM accumulator, so the result has fp32-grade accuracy at tensor-core rates.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0   TMA producer  - cp.async.bulk.tensor: A box (64 ch x R rows x NB clips) per plane, with the tap
 //                            shift folded into the row coordinate (im2col-free; padding rows are TMA zero fill),
 //                            W box (64 ch x BN rows) per plane; 128B-swizzled K-major smem tiles; mbarrier ring
 //   warp 1   MMA issuer    - one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
 //                            tcgen05.commit releases smem stages / publishes the accumulator; owns TMEM alloc
-//   warps 2-5 epilogue     - tcgen05.ld (32 lanes x 32 columns) -> bias / residual / activation -> fp32 store
-//                            and/or bf16 split planes for the next GEMM
+//   warps 2-9 epilogue     - tcgen05.ld (32 lanes x 32 columns) -> smem transpose -> bias / residual /
+//                            activation -> coalesced fp32 store and/or bf16 split planes for the next GEMM
 // Contract and reference call sites: include/pm_emage.h (pm_tapgemm_tc).
 #include <cuda.h>
 #include <stdlib.h>
@@ -27,7 +27,7 @@ constexpr int BM = 128;             // tile rows (UMMA M)
 constexpr int BK = 64;              // bf16 channels per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KB per plane
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 
 struct TcParams {
@@ -215,24 +215,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       if (n_iter > 0) tc_commit(smem_u32(acc_bar));      // accumulator complete
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  Storing that directly makes every
-    // warp store touch 32 different lines (measured: 12.5 us of a 16 us GEMM, profiles/gemm_microbench_r1.md), so the
-    // 32x32 chunk is transposed through shared memory (the operand ring is idle by now) and written with each
-    // quarter-warp covering one contiguous 128-byte row segment.
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  The 32x32 chunk is transposed
+    // through shared memory (the operand ring is idle by now) so that each quarter-warp writes one contiguous
+    // 128-byte row segment.  Measured (profiles/gemm_microbench_r1.md): with 4 warps and branchy per-element code
+    // the epilogue cost 12 us of a 16 us GEMM - it is instruction-latency bound (one warp per scheduler), not
+    // memory bound - hence 8 warps, branch-free activation (identity == leaky with slope 1) and a warp-uniform
+    // fast path for full chunks.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     if (!(p.dbg & 4)) mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
     constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
-    const uint32_t stage = smem_u32(tiles) + q * 32 * ST * 4;      // 4.6 KB per warp (shared-space address)
+    const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // 4.6 KB per warp (shared-space address)
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;              // this lane's row-in-group / first column of its float4
     const int r_shift = 31 - __clz(p.R);                           // R is a power of two
     const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
     const bool vec_r = p.residual && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
     const bool vec_b = p.out_bf16 && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0) &&
                        ((p.ob_bs & 3) == 0) && ((p.ob_ps & 3) == 0);
+    const bool all_vec = (!p.out_f32 || vec_f) && (!p.residual || vec_r) && (!p.out_bf16 || vec_b);
+    const float act_slope = p.act == PM_ACT_NONE ? 1.f : (p.act == PM_ACT_RELU ? 0.f : p.slope);
+    // rows this lane stores (8 per chunk): offsets are chunk-invariant
+    long long off_f[8], off_r[8], off_b[8];
+    uint32_t row_ok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rt = q * 32 + 4 * i + sub_r;
+      const int b = b0 + (rt >> r_shift), l = l0 + (rt & (p.R - 1));
+      if (b < p.batch && l < p.rows_out) row_ok |= 1u << i;
+      off_f[i] = (long long)b * p.o_bs + (long long)l * p.ldo;
+      off_r[i] = (long long)b * p.r_bs + (long long)l * p.ldr;
+      off_b[i] = (long long)b * p.ob_bs + (long long)l * p.ldob;
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < ((p.dbg & 6) ? 0 : BN); c0 += 32) {
+    for (int c0 = half * (BN / 2); c0 < ((p.dbg & 6) ? 0 : (half + 1) * (BN / 2)); c0 += 32) {
       uint32_t acc[32];
       float v[32];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -252,74 +269,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       }
       const int nb = n0 + c0;                                                      // first column of this chunk
       if (nb >= p.cout || (p.dbg & 1)) continue;                                   // warp-uniform
-      if (p.dbg & 16) {                                                            // experiment: row-per-thread raw stores
-        const int rt = q * 32 + lane;
-        float* of = p.out_f32 + (long long)(b0 + (rt >> r_shift)) * p.o_bs + (long long)(l0 + (rt & (p.R - 1))) * p.ldo + nb;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(of + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        continue;
-      }
       // transpose: thread = row -> smem[row][0..31]
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int n = nb + c4;                                                       // this lane's first column
-      const bool full4 = n + 4 <= p.cout;
+      const bool fast = all_vec && nb + 32 <= p.cout;                              // warp-uniform: whole chunk inside cout
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) {
-        if (full4) bias4 = make_float4(__ldg(p.bias + n), __ldg(p.bias + n + 1), __ldg(p.bias + n + 2), __ldg(p.bias + n + 3));
-        else {
-          if (n < p.cout) bias4.x = __ldg(p.bias + n);
-          if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
-          if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
-        }
+        if (n < p.cout) bias4.x = __ldg(p.bias + n);
+        if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
+        if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
+        if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
       }
-#pragma unroll 2
+      // identity == leaky with slope 1: one branch-free formula for none / relu / leaky / partial activation
+      const float s0 = n < p.act_cols ? act_slope : 1.f, s1 = n + 1 < p.act_cols ? act_slope : 1.f;
+      const float s2 = n + 2 < p.act_cols ? act_slope : 1.f, s3 = n + 3 < p.act_cols ? act_slope : 1.f;
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int rt = q * 32 + 4 * i + sub_r;                                     // tile row
-        const int b = b0 + (rt >> r_shift);
-        const int l = l0 + (rt & (p.R - 1));
-        if (b >= p.batch || l >= p.rows_out || n >= p.cout) continue;
+        if (!((row_ok >> i) & 1u)) continue;
         float4 x = lds128(stage + ((4 * i + sub_r) * ST + c4) * 4);
         x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-        if (p.residual) {
-          const float* rs = p.residual + (long long)b * p.r_bs + (long long)l * p.ldr + n;
-          if (vec_r && full4) {
-            const float4 t = *reinterpret_cast<const float4*>(rs);
+        if (fast) {
+          if (p.residual) {
+            const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
-          } else {
-            x.x += rs[0];
-            if (n + 1 < p.cout) x.y += rs[1];
-            if (n + 2 < p.cout) x.z += rs[2];
-            if (n + 3 < p.cout) x.w += rs[3];
           }
-        }
-        if (p.act != PM_ACT_NONE) {
-          if (n < p.act_cols) x.x = pm_act(x.x, p.act, p.slope);
-          if (n + 1 < p.act_cols) x.y = pm_act(x.y, p.act, p.slope);
-          if (n + 2 < p.act_cols) x.z = pm_act(x.z, p.act, p.slope);
-          if (n + 3 < p.act_cols) x.w = pm_act(x.w, p.act, p.slope);
-        }
-        if (p.out_f32) {
-          float* of = p.out_f32 + (long long)b * p.o_bs + (long long)l * p.ldo + n;
-          if (p.dbg & 8) {                                   // experiment: everything but the store itself
-            if (x.x == 1.2345e38f) *reinterpret_cast<float4*>(of) = x;
-          } else if (vec_f && full4) *reinterpret_cast<float4*>(of) = x;
-          else {
-            of[0] = x.x;
-            if (n + 1 < p.cout) of[1] = x.y;
-            if (n + 2 < p.cout) of[2] = x.z;
-            if (n + 3 < p.cout) of[3] = x.w;
+          x.x = fmaxf(x.x, 0.f) + s0 * fminf(x.x, 0.f);
+          x.y = fmaxf(x.y, 0.f) + s1 * fminf(x.y, 0.f);
+          x.z = fmaxf(x.z, 0.f) + s2 * fminf(x.z, 0.f);
+          x.w = fmaxf(x.w, 0.f) + s3 * fminf(x.w, 0.f);
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off_f[i] + n) = x;
+          if (p.out_bf16) {
+            const PmPlanes P{p.out_bf16 + off_b[i], p.ob_ps, p.ldob, p.out_nsplit};
+            pm_store_planes4(P, 0, n, x);
           }
-        }
-        if (p.out_bf16) {
-          const PmPlanes P{p.out_bf16 + (long long)b * p.ob_bs, p.ob_ps, p.ldob, p.out_nsplit};
-          if (vec_b && full4) pm_store_planes4(P, l, n, x);
-          else {
-            pm_store_planes(P, l, n, x.x);
-            if (n + 1 < p.cout) pm_store_planes(P, l, n + 1, x.y);
-            if (n + 2 < p.cout) pm_store_planes(P, l, n + 2, x.z);
-            if (n + 3 < p.cout) pm_store_planes(P, l, n + 3, x.w);
+        } else if (n < p.cout) {                                                   // ragged / unaligned tail: per element
+          float xs[4] = {x.x, x.y, x.z, x.w};
+          const float ss[4] = {s0, s1, s2, s3};
+          const PmPlanes P{p.out_bf16 ? p.out_bf16 + off_b[i] : nullptr, p.ob_ps, p.ldob, p.out_nsplit};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (n + k >= p.cout) break;
+            float y = xs[k];
+            if (p.residual) y += p.residual[off_r[i] + n + k];
+            y = fmaxf(y, 0.f) + ss[k] * fminf(y, 0.f);
+            if (p.out_f32) p.out_f32[off_f[i] + n + k] = y;
+            if (P.ptr) pm_store_planes(P, 0, n + k, y);
           }
         }
       }
