@@ -16,6 +16,7 @@
 //                            activation -> coalesced fp32 store and/or bf16 split planes for the next GEMM
 // Contract and reference call sites: include/pm_emage.h (pm_tapgemm_tc).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "pm_common.cuh"
@@ -41,6 +42,7 @@ struct TcParams {
   float* out_f32; long long o_bs; int ldo;
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
+  int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
   int dbg;   // tuning experiments only (PM_TC_DBG): 1 = no global stores, 2 = no epilogue, 4 = no TMA / MMA
 };
 
@@ -86,6 +88,28 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -145,13 +169,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
   const int n_iter = (p.dbg & 4) ? 0 : p.taps * p.kblocks;
+  // thread-block cluster: CTAs of one cluster share operand tiles through TMA multicast
+  const bool clustered = p.cm * p.cn > 1;
+  const uint32_t crank = clustered ? cluster_ctarank() : 0;
+  const int rx = (int)crank % p.cm, ry = (int)crank / p.cm;
+  uint16_t mask_w = 0, mask_a = 0;                              // CTAs that receive my W slice / my A slice
+  for (int i = 0; i < p.cm; ++i) mask_w |= (uint16_t)(1u << (ry * p.cm + i));
+  for (int j = 0; j < p.cn; ++j) mask_a |= (uint16_t)(1u << (rx + j * p.cm));
+  const uint16_t mask_all = mask_w | mask_a;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), (uint32_t)(p.cm + p.cn - 1));   // every CTA that writes into this stage
     }
     mbar_init(smem_u32(acc_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,6 +194,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -178,9 +211,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         mbar_expect_tx(bar, tx);
         uint8_t* st = tiles + (size_t)s * stage_bytes;
         for (int pl = 0; pl < p.nsplit; ++pl) {
-          tma_load_4d(smem_u32(st + pl * A_TILE_BYTES), &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
-          tma_load_3d(smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES), &map_w, bar, kb * BK,
-                      tap * p.w_rows + n0, pl);
+          const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
+          const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
+          if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+          else {                                   // my 128/cn-row slice of the A tile, to every CTA of my tile row
+            const int ar = BM / p.cn;
+            tma_load_4d_mc(a_dst + ry * ar * 128, &map_a, bar, kb * BK, l0 + tap - p.pad + ry * ar, b0, pl, mask_a);
+          }
+          if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
+          else {                                   // my BN/cm-row slice of the W tile, to every CTA of my tile column
+            const int wr = BN / p.cm;
+            tma_load_3d_mc(w_dst + rx * wr * 128, &map_w, bar, kb * BK, tap * p.w_rows + n0 + rx * wr, pl, mask_w);
+          }
         }
       }
     }
@@ -210,7 +252,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             }
           }
         }
-        tc_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
+        if (clustered) tc_commit_mc(smem_u32(&empty_bar[s]), mask_all);   // free the stage in every CTA that fills it
+        else tc_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs have read it
       }
       if (n_iter > 0) tc_commit(smem_u32(acc_bar));      // accumulator complete
     }
@@ -325,6 +368,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   // teardown: everyone done with TMEM before the owning warp frees it
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();        // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -402,6 +446,22 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
+  if (p.cm * p.cn > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cm;
+    attr[0].val.clusterDim.y = p.cn;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN>, ma, mw, p);
+    return e == cudaSuccess ? PM_OK : (int)e;
+  }
   tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
   PM_LAUNCH_CHECK();
 }
@@ -447,6 +507,15 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ob_ps = ob_ps; p.ob_bs = ob_bs; p.ldob = ldob;
   p.out_nsplit = out_bf16 ? out_nsplit : 0;
   p.stages = 0;
+  // cluster shape: share W across 2 row tiles and A across 2 column tiles when the grid allows (R == 128 only)
+  {
+    static const char* env_cl = getenv("PM_TC_CLUSTER");          // "cm,cn" tuning override, e.g. "1,1" = off
+    int want_m = 2, want_n = 2;
+    if (env_cl) sscanf(env_cl, "%d,%d", &want_m, &want_n);
+    const int gx = pm_cdiv(rows_out, R), gy = pm_cdiv(cout, BNsel);
+    p.cm = (R == 128 && want_m > 1 && gx % want_m == 0 && BNsel % (8 * want_m) == 0) ? want_m : 1;
+    p.cn = (R == 128 && want_n > 1 && gy % want_n == 0) ? want_n : 1;
+  }
   static const int env_dbg = getenv("PM_TC_DBG") ? atoi(getenv("PM_TC_DBG")) : 0;
   p.dbg = env_dbg;
 
@@ -456,14 +525,14 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
     const long long ps_el = nsplit > 1 ? a_ps : bs_el * batch;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows_in, (cuuint64_t)batch, (cuuint64_t)nsplit};
     cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)R, (cuuint32_t)NB, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(R / p.cn), (cuuint32_t)NB, 1};
     if (!encode_map(&ma, A, 4, dims, strides, box)) return PM_EBADARG;
   }
   {
     const long long ps_el = nsplit > 1 ? w_ps : (long long)taps * w_rows * ldw;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps * w_rows, (cuuint64_t)nsplit};
     cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BNsel / p.cm), 1};
     if (!encode_map(&mw, W, 3, dims, strides, box)) return PM_EBADARG;
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
