@@ -71,6 +71,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// Same, for the hot loops: first probe without touching the clock; the watchdog only runs while actually waiting.
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  if (!done) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -123,10 +133,8 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
+// UMMA smem descriptors (cute::UMMA::SmemDescriptor, version 1 = sm_100): K-major, 128-byte swizzle, 8-row groups
+// 1024 B apart; built in the MMA loop as desc_hi | (addr >> 4).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -201,59 +209,84 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)stage_bytes;
+      // dbg 32 / 64: skip the W / A loads (throughput experiments; results are garbage)
+      const uint32_t tx = (uint32_t)(p.nsplit * (((p.dbg & 64) ? 0 : A_TILE_BYTES) + ((p.dbg & 32) ? 0 : W_TILE_BYTES)));
+      int s = 0, tap = 0, kb = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const int tap = it / p.kblocks, kb = it % p.kblocks;
+        mbar_wait_fast(smem_u32(&empty_bar[s]), ph ^ 1u);
         const uint32_t bar = smem_u32(&full_bar[s]);
         mbar_expect_tx(bar, tx);
         uint8_t* st = tiles + (size_t)s * stage_bytes;
         for (int pl = 0; pl < p.nsplit; ++pl) {
           const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
           const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
-          if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+          if (p.dbg & 64) {}
+          else if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
           else {                                   // my 128/cn-row slice of the A tile, to every CTA of my tile row
             const int ar = BM / p.cn;
             tma_load_4d_mc(a_dst + ry * ar * 128, &map_a, bar, kb * BK, l0 + tap - p.pad + ry * ar, b0, pl, mask_a);
           }
-          if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
+          if (p.dbg & 32) {}
+          else if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
           else {                                   // my BN/cm-row slice of the W tile, to every CTA of my tile column
             const int wr = BN / p.cm;
             tma_load_3d_mc(w_dst + rx * wr * 128, &map_w, bar, kb * BK, tap * p.w_rows + n0 + rx * wr, pl, mask_w);
           }
         }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++kb == p.kblocks) { kb = 0; ++tap; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // One thread feeds the tensor core, so its own instruction stream must stay far below the 64 cycles a
+    // 128x128x16 MMA takes.  Measured: with per-MMA descriptor construction, runtime div/mod for the stage ring
+    // and a clock-reading wait loop this thread was THE bottleneck (the mainloop ran at the same speed with all TMA
+    // loads disabled, profiles/gemm_microbench_r1.md).  Hence: running stage/phase counters, descriptors advanced by
+    // adding to a precomputed 64-bit base, product loops specialised per split mode and fully unrolled.
     if (lane == 0) {
-      uint32_t acc_main[2] = {0, 0}, acc_corr = 0;
+      const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t tiles_u32 = smem_u32(tiles);
+      const uint32_t d_corr = tmem_base + 2 * BN;
+      uint32_t first_main0 = 1, first_main1 = 1, first_corr = 1;     // 1 until the accumulator has been written once
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+        mbar_wait_fast(smem_u32(&full_bar[s]), ph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(tiles + (size_t)s * stage_bytes);
-        const uint32_t w_base = a_base + p.nsplit * A_TILE_BYTES;
-        // products ordered small -> large: (i,j) with i + j < nsplit
-        for (int sum = p.nsplit - 1; sum >= 0; --sum) {
-          for (int i = 0; i <= sum; ++i) {
-            const int j = sum - i;
-            const uint32_t a_t = a_base + i * A_TILE_BYTES, w_t = w_base + j * W_TILE_BYTES;
-            const bool corr = sum > 0;
-            const uint32_t d = tmem_base + (corr ? 2 * BN : (it & 1) * BN);
-            uint32_t& flag = corr ? acc_corr : acc_main[it & 1];
+        const uint32_t a_base = tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
+        const uint64_t a0 = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFFu);                       // A plane 0, k = 0
+        const uint64_t w0 = desc_hi | (uint64_t)(((a_base + p.nsplit * A_TILE_BYTES) >> 4) & 0x3FFFu);
+        constexpr uint64_t A_PL = A_TILE_BYTES >> 4, W_PL = W_TILE_BYTES >> 4, K_ST = (UMMA_K * 2) >> 4;   // descriptor units
+        const bool odd = it & 1;
+        const uint32_t d_main = tmem_base + (odd ? BN : 0);
+        // cross products first (small -> large), into the correction accumulator
+        if (p.nsplit == 3) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              tc_mma_bf16(d, umma_desc(a_t + k * UMMA_K * 2), umma_desc(w_t + k * UMMA_K * 2), IDESC, flag);
-              flag = 1;
-            }
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + 2 * W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
+          first_corr = 0;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + W_PL + k * K_ST, IDESC, 1);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + 2 * A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
+        }
+        if (p.nsplit >= 2) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
+          first_corr = 0;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
+        }
+        {
+          const uint32_t first = odd ? first_main1 : first_main0;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_main, a0 + k * K_ST, w0 + k * K_ST, IDESC, (k | (int)(first ^ 1u)) != 0);
+          if (odd) first_main1 = 0; else first_main0 = 0;
         }
         if (clustered) tc_commit_mc(smem_u32(&empty_bar[s]), mask_all);   // free the stage in every CTA that fills it
         else tc_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs have read it
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       if (n_iter > 0) tc_commit(smem_u32(acc_bar));      // accumulator complete
     }
