@@ -540,10 +540,13 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ob_ps = ob_ps; p.ob_bs = ob_bs; p.ldob = ldob;
   p.out_nsplit = out_bf16 ? out_nsplit : 0;
   p.stages = 0;
-  // cluster shape: share W across 2 row tiles and A across 2 column tiles when the grid allows (R == 128 only)
+  // Thread-block clusters with TMA multicast (W shared across cm row tiles, A across cn column tiles) are
+  // implemented and tested but OFF by default: measured on B200 the mainloop is bound by the tensor pipe and the
+  // per-stage barrier round trip, not by L2->smem traffic, and 2x2 clusters were 10-25 % slower
+  // (profiles/gemm_microbench_r1.md).  PM_TC_CLUSTER="cm,cn" turns them on (R == 128 grids only).
   {
-    static const char* env_cl = getenv("PM_TC_CLUSTER");          // "cm,cn" tuning override, e.g. "1,1" = off
-    int want_m = 2, want_n = 2;
+    static const char* env_cl = getenv("PM_TC_CLUSTER");
+    int want_m = 1, want_n = 1;
     if (env_cl) sscanf(env_cl, "%d,%d", &want_m, &want_n);
     const int gx = pm_cdiv(rows_out, R), gy = pm_cdiv(cout, BNsel);
     p.cm = (R == 128 && want_m > 1 && gx % want_m == 0 && BNsel % (8 * want_m) == 0) ? want_m : 1;
