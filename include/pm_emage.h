@@ -53,7 +53,9 @@ int pm_tapgemm_f32(const float* A, long long a_bs, int lda, int batch, int rows_
  * of 8 elements (TMA 16-byte rule).  The activation is applied to columns < act_cols only (<=0: all).
  * The epilogue writes the fp32 result and/or its bf16 split planes (out_f32 / out_bf16 nullable).
  * Operands are staged by TMA (cp.async.bulk.tensor, zero fill for padding rows, tap shift folded into the
- * row coordinate); descriptors are built on the host inside this call from the raw pointers. */
+ * row coordinate); descriptors are built on the host inside this call from the raw pointers.
+ * `prefetch` (nullable, 16-byte aligned): prefetch_bytes of global memory - the NEXT GEMM's packed weights - are
+ * pulled into L2 by this launch (cp.async.bulk.prefetch.L2), so weight streaming overlaps the previous GEMM. */
 int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, int batch, int rows_in, int cin,
                   const uint16_t* W, long long w_ps, int w_rows, int ldw, int taps, int pad, int nsplit,
                   const float* bias, int rows_out, int cout,
@@ -61,7 +63,7 @@ int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, in
                   int act, int act_cols, float slope,
                   float* out_f32, long long o_bs, int ldo,
                   uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
-                  void* stream);
+                  const void* prefetch, long long prefetch_bytes, void* stream);
 
 /* fp32 (batch, rows, ch) -> nsplit bf16 planes (round-to-nearest hi, then residual planes). */
 int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,

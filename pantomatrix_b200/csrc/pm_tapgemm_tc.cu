@@ -42,6 +42,7 @@ struct TcParams {
   float* out_f32; long long o_bs; int ldo;
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
+  const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
   int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
   int dbg;   // tuning experiments only (PM_TC_DBG): 1 = no global stores, 2 = no epilogue, 4 = no TMA / MMA
 };
@@ -208,6 +209,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 
   if (warp == 0) {
     // ===== TMA producer =====
+    if (lane == 1 && p.prefetch) {
+      // Weights are read once per window and the per-window set (0.6-0.8 GB) does not fit the 126 MB L2, so every
+      // GEMM would stream its W tiles from HBM at DRAM latency with only 2-3 stages in flight.  Each CTA instead
+      // prefetches its share of the NEXT GEMM's weights into L2 (cp.async.bulk.prefetch.L2) while this one computes.
+      const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
+      const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      long long share = ((p.prefetch_bytes + ncta - 1) / ncta + 127) & ~127LL;
+      long long off = cta * share;
+      long long end = off + share < p.prefetch_bytes ? off + share : p.prefetch_bytes;
+      end &= ~15LL;
+      for (; off < end; off += 16384) {
+        const uint32_t n = (uint32_t)(end - off < 16384 ? end - off : 16384);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.prefetch + off), "r"(n) : "memory");
+      }
+    }
     if (lane == 0) {
       // dbg 32 / 64: skip the W / A loads (throughput experiments; results are garbage)
       const uint32_t tx = (uint32_t)(p.nsplit * (((p.dbg & 64) ? 0 : A_TILE_BYTES) + ((p.dbg & 32) ? 0 : W_TILE_BYTES)));
@@ -508,8 +524,9 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
                              int act, int act_cols, float slope,
                              float* out_f32, long long o_bs, int ldo,
                              uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
-                             void* stream) {
+                             const void* prefetch, long long prefetch_bytes, void* stream) {
   PM_REQUIRE(A && W && (out_f32 || out_bf16));
+  PM_REQUIRE(!prefetch || (prefetch_bytes >= 0 && (reinterpret_cast<uintptr_t>(prefetch) & 15) == 0));
   PM_REQUIRE(batch > 0 && rows_in > 0 && rows_out > 0 && cin > 0 && cout > 0 && taps > 0);
   PM_REQUIRE(nsplit >= 1 && nsplit <= 3 && (!out_bf16 || (out_nsplit >= 1 && out_nsplit <= 3)));
   PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_LEAKY);
@@ -540,6 +557,8 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); p.ob_ps = ob_ps; p.ob_bs = ob_bs; p.ldob = ldob;
   p.out_nsplit = out_bf16 ? out_nsplit : 0;
   p.stages = 0;
+  p.prefetch = static_cast<const uint8_t*>(prefetch);
+  p.prefetch_bytes = prefetch ? prefetch_bytes : 0;
   // Thread-block clusters with TMA multicast (W shared across cm row tiles, A across cn column tiles) are
   // implemented and tested but OFF by default: measured on B200 the mainloop is bound by the tensor pipe and the
   // per-stage barrier round trip, not by L2->smem traffic, and 2x2 clusters were 10-25 % slower

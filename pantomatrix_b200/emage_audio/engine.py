@@ -106,11 +106,23 @@ class _Fork:
 
 class _Conv:
     """One Conv1d / Linear: fp32 tap-major weights (taps, cout, cin) + lazily packed bf16 planes."""
-    __slots__ = ("w", "b", "stride", "pad", "_packed")
+    __slots__ = ("w", "b", "stride", "pad", "_packed", "_next")
 
     def __init__(self, w, b, stride=1, pad=0):
         self.w, self.b, self.stride, self.pad = w, b, stride, pad
         self._packed = {}
+        self._next = None          # the GEMM that followed this one last time (learned; see _prefetch_hint)
+
+    def _prefetch_hint(self, ns):
+        """Weights are read once per window and do not fit L2, so each GEMM prefetches the NEXT GEMM's packed
+        weights into L2 while it runs.  The schedule is static, so "next" is simply whichever GEMM was issued
+        after this one on the previous pass (a wrong guess only costs a useless prefetch)."""
+        prev = _STATE.get("prev_conv")
+        if prev is not None and prev is not self:
+            prev._next = self
+        _STATE["prev_conv"] = self
+        nxt = self._next
+        return nxt._packed[ns].t if (nxt is not None and ns in nxt._packed) else None
 
     def packed(self, nsplit):
         """bf16 planes for the tensor-core engine.  A stride-s conv is packed as the equivalent stride-1 conv
@@ -140,6 +152,7 @@ class _Conv:
         taps, cout, _ = self.w.shape
         s = self.stride
         want_f, out_ns = "f" in want, (ns if "p" in want else 0)
+        pf = self._prefetch_hint(ns)
         if s == 1:
             a = _planes(x, ns)
             batch, rows = a.batch, a.rows
@@ -152,12 +165,13 @@ class _Conv:
                 _, pl = ops.tapgemm_tc(a.flat(), self.packed(ns), self.b, rows_out=batch * rows, act=act, slope=slope,
                                        want_f32=want_f, out=None if out is None else out.view(1, batch * rows, cout),
                                        residual=None if residual is None else residual.view(1, batch * rows, cout),
-                                       out_nsplit=out_ns, out_slack=out_slack)
+                                       out_nsplit=out_ns, out_slack=out_slack, prefetch=pf)
                 if pl is not None:                         # back to the (clips, rows) view
                     pl = ops.Planes(pl.t.view(pl.t.shape[0], batch, rows, pl.t.shape[3]), rows, cout, pl.slack)
             else:
                 _, pl = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, pad=self.pad, act=act, slope=slope,
-                                       residual=residual, want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack)
+                                       residual=residual, want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack,
+                                       prefetch=pf)
             return out if want == "f" else ops.Act(out, pl)
         assert self.pad == 0
         a = _planes(x, ns, need_slack=s)
@@ -165,7 +179,7 @@ class _Conv:
         assert a.t.stride(2) == cin and a.t.stride(1) == rows * cin, "strided view needs dense (clips*rows, C) planes"
         rows_out = (rows - taps) // s + 1
         o, pl = ops.tapgemm_tc(a, self.packed(ns), self.b, rows_out=rows_out, act=act, slope=slope, residual=residual,
-                               want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack,
+                               want_f32=want_f, out=out, out_nsplit=out_ns, out_slack=out_slack, prefetch=pf,
                                a_view=(-(-rows // s), s * cin, s * cin))
         return o if want == "f" else ops.Act(o, pl)
 

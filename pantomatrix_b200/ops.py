@@ -316,8 +316,9 @@ class PackedW:
 
 
 def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0,
-               residual=None, want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0):
-    """Tensor-core tap-GEMM.  `a_view` = (rows_in, cin, lda) overrides the logical view of the A planes
+               residual=None, want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0, prefetch=None):
+    """Tensor-core tap-GEMM.  `prefetch`: a tensor (the next GEMM's packed weights) to pull into L2 meanwhile.
+    `a_view` = (rows_in, cin, lda) overrides the logical view of the A planes
     (strided convs pass the (rows/s, s*C) view of the same memory).  Returns (fp32 out | None, Planes | None)."""
     t = a.t
     nsplit, batch = t.shape[0], t.shape[1]
@@ -345,5 +346,7 @@ def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, ac
           _ptr(bias), rows_out, cout, _ptr(residual), r_bs, ldr, act, act_cols, float(slope),
           _ptr(out_f), o_bs, ldo,
           None if out_p is None else out_p.t.data_ptr(), 0 if out_p is None else out_p.t.stride(0),
-          0 if out_p is None else out_p.t.stride(1), 0 if out_p is None else out_p.t.stride(2), out_nsplit, _stream())
+          0 if out_p is None else out_p.t.stride(1), 0 if out_p is None else out_p.t.stride(2), out_nsplit,
+          None if prefetch is None else prefetch.data_ptr(),
+          0 if prefetch is None else prefetch.numel() * prefetch.element_size(), _stream())
     return out_f, out_p

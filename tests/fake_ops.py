@@ -156,7 +156,7 @@ def split_bf16(x, nsplit, slack_rows=0):
 
 
 def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_cols=0, slope=0.0, residual=None,
-               want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0):
+               want_f32=True, out_nsplit=0, out=None, a_view=None, out_slack=0, prefetch=None):
     t = a.t
     nsplit, batch = t.shape[0], t.shape[1]
     rows_a, cin, lda = (a.rows, a.ch, t.stride(2)) if a_view is None else a_view
