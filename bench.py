@@ -93,7 +93,7 @@ class ClockSampler:
 
 def time_cpu_oracle(sample_clips, repeats, warmup):
     """Times oracle.emage_generate (the CPU port of the reference path) on `sample_clips` x 10 s clips.
-    The thread count is the best of a quick probe over {all cores, 64, 32, 16, 8}: on many-core hosts the
+    The thread count is the best of a quick probe over {min(cores,64), 32, 16, 8}: on many-core hosts the
     small per-window ops of this model run slower with every core than with a subset, and the baseline
     should be the CPU at its best.  Returns (frames per run, [seconds per run], threads used)."""
     import torch
@@ -109,13 +109,14 @@ def time_cpu_oracle(sample_clips, repeats, warmup):
             O.emage_generate(sd, cfg, vq, audio, torch.zeros(clips, 1, dtype=torch.long))
         return time.perf_counter() - t0
 
-    best, best_t = cores, None
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
+    best, best_t = min(cores, 16), None
+    cands = sorted({c for c in (min(cores, 64), 32, 16, 8) if c <= cores}, reverse=True)
     if len(cands) > 1:
-        for c in cands:
+        torch.set_num_threads(cands[0])
+        run(1)                                       # warm-up: allocator, oneDNN primitive caches
+        for c in cands:                              # (all-core runs on 100+ core hosts are 10x slower: not probed)
             torch.set_num_threads(c)
-            run(1)                                   # warm the thread pool / allocator at this width
-            t = run(2)
+            t = run(1)
             if best_t is None or t < best_t:
                 best, best_t = c, t
     torch.set_num_threads(best)
