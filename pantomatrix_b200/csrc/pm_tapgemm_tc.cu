@@ -82,6 +82,14 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   if (!done) mbar_wait(bar, parity);
 }
+// One lane of a converged warp (PTX elect.sync): the canonical guard for TMA / tcgen05 issue.  With warp-uniform
+// control flow around it the compiler keeps descriptors and barrier addresses in uniform registers; guarding with
+// `lane == 0` instead makes them thread-varying and wraps every UTMALDG / UTCHMMA in a waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -224,16 +232,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.prefetch + off), "r"(n) : "memory");
       }
     }
-    if (lane == 0) {
+    {
       // dbg 32 / 64: skip the W / A loads (throughput experiments; results are garbage)
       const uint32_t tx = (uint32_t)(p.nsplit * (((p.dbg & 64) ? 0 : A_TILE_BYTES) + ((p.dbg & 32) ? 0 : W_TILE_BYTES)));
       int s = 0, tap = 0, kb = 0;
       uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        mbar_wait_fast(smem_u32(&empty_bar[s]), ph ^ 1u);
+        mbar_wait_fast(smem_u32(&empty_bar[s]), ph ^ 1u);       // whole warp waits (uniform control flow)
         const uint32_t bar = smem_u32(&full_bar[s]);
-        mbar_expect_tx(bar, tx);
         uint8_t* st = tiles + (size_t)s * stage_bytes;
+        if (elect_one()) {
+        mbar_expect_tx(bar, tx);
         for (int pl = 0; pl < p.nsplit; ++pl) {
           const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
           const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
@@ -250,6 +259,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             tma_load_3d_mc(w_dst + rx * wr * 128, &map_w, bar, kb * BK, tap * p.w_rows + n0 + rx * wr, pl, mask_w);
           }
         }
+        }
+        __syncwarp();
         if (++s == p.stages) { s = 0; ph ^= 1u; }
         if (++kb == p.kblocks) { kb = 0; ++tap; }
       }
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     // and a clock-reading wait loop this thread was THE bottleneck (the mainloop ran at the same speed with all TMA
     // loads disabled, profiles/gemm_microbench_r1.md).  Hence: running stage/phase counters, descriptors advanced by
     // adding to a precomputed 64-bit base, product loops specialised per split mode and fully unrolled.
-    if (lane == 0) {
+    {
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t tiles_u32 = smem_u32(tiles);
       const uint32_t d_corr = tmem_base + 2 * BN;
@@ -269,8 +280,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        mbar_wait_fast(smem_u32(&full_bar[s]), ph);
+        mbar_wait_fast(smem_u32(&full_bar[s]), ph);               // whole warp waits (uniform control flow)
         tc_fence_after();
+        if (elect_one()) {
         const uint32_t a_base = tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
         const uint64_t a0 = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFFu);                       // A plane 0, k = 0
         const uint64_t w0 = desc_hi | (uint64_t)(((a_base + p.nsplit * A_TILE_BYTES) >> 4) & 0x3FFFu);
@@ -281,16 +293,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         if (p.nsplit == 3) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + 2 * W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
-          first_corr = 0;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + W_PL + k * K_ST, IDESC, 1);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + 2 * A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
         }
         if (p.nsplit >= 2) {
+          const uint32_t fresh = p.nsplit == 3 ? 0u : first_corr;      // with 3 planes the block above already wrote it
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
-          first_corr = 0;
+          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + W_PL + k * K_ST, IDESC, (k | (int)(fresh ^ 1u)) != 0);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
         }
@@ -298,13 +309,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           const uint32_t first = odd ? first_main1 : first_main0;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_main, a0 + k * K_ST, w0 + k * K_ST, IDESC, (k | (int)(first ^ 1u)) != 0);
-          if (odd) first_main1 = 0; else first_main0 = 0;
         }
         if (clustered) tc_commit_mc(smem_u32(&empty_bar[s]), mask_all);   // free the stage in every CTA that fills it
         else tc_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs have read it
+        }
+        __syncwarp();
+        if (p.nsplit >= 2) first_corr = 0;
+        if (it & 1) first_main1 = 0; else first_main0 = 0;
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      if (n_iter > 0) tc_commit(smem_u32(acc_bar));      // accumulator complete
+      if (n_iter > 0 && elect_one()) tc_commit(smem_u32(acc_bar));      // accumulator complete
     }
   } else {
     // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
