@@ -49,7 +49,10 @@ def wav_out_len(n: int) -> int:
 # Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores
 # with plain bf16 / bf16x3 / bf16x6 split operands (see csrc/pm_tapgemm_tc.cu).
 PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3}
-_STATE = {"nsplit": PRECISIONS["fp32"], "fork": True}      # fork: overlap independent branches on side streams
+# Default: bf16x6 - the tensor-core mode that meets the fp32 parity gates.  "fp32" selects the
+# exact-order SIMT engine, "bf16x3" / "bf16" trade accuracy for speed.  PM_EMAGE_PRECISION overrides the default.
+DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "bf16x6")
+_STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True}   # fork: overlap independent branches on side streams
 
 
 def set_precision(name: str) -> None:

@@ -25,6 +25,16 @@ def product():
     return build_product(seed=0)
 
 
+@pytest.fixture(autouse=True)
+def _exact_engine_by_default():
+    """Tests run on the exact-order fp32 engine unless they select a tensor-core mode themselves (the product
+    default is bf16x6; it is exercised by the `precision` parametrisations below)."""
+    from pantomatrix_b200.emage_audio import engine
+    engine.set_precision("fp32")
+    yield
+    engine.set_precision(engine.DEFAULT_PRECISION)
+
+
 @pytest.fixture(scope="module")
 def ckpt():
     return make_checkpoint(seed=0)
@@ -78,10 +88,13 @@ def _face_ties(vqm, vq, lat, want_lat, tag, max_ties=0):
     return ~near
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x6"])
 @pytest.mark.parametrize("case", GOLDEN)
-def test_matches_reference_golden(case, product, golden_dir):
+def test_matches_reference_golden(case, precision, product, golden_dir):
+    from pantomatrix_b200.emage_audio import engine
     from pantomatrix_b200.pipeline import generate
     model, vqm = product
+    engine.set_precision(precision)
     g = np.load(os.path.join(golden_dir, f"case_{case}.npz"))
     bs, n = int(g["bs"]), int(g["n_samples"])
     audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"]))).cuda()

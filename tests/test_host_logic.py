@@ -24,6 +24,8 @@ def cpu_product(monkeypatch):
         if not name.startswith("_") and callable(getattr(fake_ops, name)) and hasattr(real, name):
             monkeypatch.setattr(real, name, getattr(fake_ops, name))
     monkeypatch.setattr(modeling, "_require_cuda", lambda module, what: torch.device("cpu"))
+    from pantomatrix_b200.emage_audio import engine
+    monkeypatch.setitem(engine._STATE, "nsplit", 0)      # exact fp32 engine unless a test selects a tensor-core mode
     return build_product(seed=0, device="cpu")
 
 
@@ -88,10 +90,7 @@ def test_tensor_core_schedule_host_logic(cpu_product, golden_dir, precision, ato
     g = np.load(os.path.join(golden_dir, "case_tail11.npz"))
     audio = torch.from_numpy(synth_audio(int(g["bs"]), int(g["n_samples"]), int(g["audio_seed"])))
     engine.set_precision(precision)
-    try:
-        lat, pred = generate(model, vqm, audio)
-    finally:
-        engine.set_precision("fp32")
+    lat, pred = generate(model, vqm, audio)          # (the cpu_product fixture restores the engine state)
     for p in PARTS:
         np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=atol, rtol=0)
         agree = (lat["cls_" + p].argmax(-1).numpy() == g["idx_cls_" + p]).mean()

@@ -48,6 +48,8 @@ def _worker(rank, world, port, out_path):
         if not name.startswith("_") and callable(getattr(fake_ops, name)) and hasattr(real, name):
             setattr(real, name, getattr(fake_ops, name))
     modeling._require_cuda = lambda module, what: torch.device("cpu")
+    from pantomatrix_b200.emage_audio import engine
+    engine.set_precision("fp32")
     # each rank starts from a DIFFERENT checkpoint; after the broadcast both must hold rank 0's
     model, vqm = build_product(seed=rank, device="cpu")
     nbytes = sharding.broadcast_checkpoint(model, vqm, src=0)
@@ -82,6 +84,8 @@ def test_two_rank_sharded_generate_matches_single_process(tmp_path, monkeypatch)
         if not name.startswith("_") and callable(getattr(fake_ops, name)) and hasattr(real, name):
             monkeypatch.setattr(real, name, getattr(fake_ops, name))
     monkeypatch.setattr(modeling, "_require_cuda", lambda module, what: torch.device("cpu"))
+    from pantomatrix_b200.emage_audio import engine
+    monkeypatch.setitem(engine._STATE, "nsplit", 0)
     model, vqm = build_product(seed=0, device="cpu")
     lat, pred = generate(model, vqm, torch.from_numpy(synth_audio(3, 21600, 77)))
     assert got["aa"].shape == pred["motion_axis_angle"].shape
