@@ -130,5 +130,19 @@ def main():
               "face-l2:", len(np.unique(out["idx_l2_face"])))
 
 
+def upsample_golden():
+    """Golden for the output writer's linear upsampler: executes the REFERENCE's own time_upsample_numpy.  The
+    module emage_utils/motion_io.py cannot be imported here (it imports smplx at line 3), so only that function
+    is compiled out of the reference source with ast - nothing is copied into the repo."""
+    import ast
+    src = open(os.path.join(REF, "emage_utils", "motion_io.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "time_upsample_numpy"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_motion_io", "exec"), ns)
+    x = np.random.default_rng(7).standard_normal((2, 7, 5))
+    np.savez(os.path.join(HERE, "upsample.npz"), x=x, **{f"k{k}": ns["time_upsample_numpy"](x, k) for k in (1, 2, 3)})
+
+
 if __name__ == "__main__":
     main()
+    upsample_golden()
