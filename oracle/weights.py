@@ -42,6 +42,13 @@ VQ_CFGS = {
 }
 
 
+LSTM_CFG = dict(
+    pose_fps=15, motion_f=256, pose_dims=258, pose_rep="smplx", body_dims=78, hands_dims=180, audio_rep="wave16k",
+    audio_sr=16000, audio_fps=16000, audio_norm=False, audio_f=128, speaker_f=16, speaker_dims=1, hidden_size=512,
+    n_layer=4, dropout_prob=0.1, seed_frames=4, joint_mask="local_upper",
+)      # configs/camn_audio.yaml:27-47 == configs/disco_audio.yaml:26-46 (model block)
+
+
 # Gains that keep the time-varying (audio-driven) part of the activations comparable to the
 # constant part, so emitted code indices are diverse (first matching substring wins).
 _GAINS = (
@@ -50,6 +57,8 @@ _GAINS = (
     ("audio_encoder_", 1.2),
     ("motion_encoder.", 1.4),
     ("_cls", 1.5),
+    ("body_out.fc", 3.0),                           # CaMN / DisCo rot6d heads
+    ("hands_out.fc", 3.0),
     ("audio_face_motion_proj", 4.0),                # memory scale => audio-driven face variation
     ("face_motion_decoder.", 2.0),
 )
@@ -75,6 +84,11 @@ def synth_tensor(name: str, shape, seed: int = 0, tag: str = "") -> np.ndarray |
         return (0.1 * g.standard_normal(shape)).astype(np.float32)
     if "quantizer.embedding" in name:                      # VQ codebook rows
         return g.standard_normal(shape).astype(np.float32)
+    if "_motion_decoder.weight_" in name:                  # LSTM matrices: keep the gates away from saturation
+        fan_in = int(shape[1])
+        return (g.standard_normal(shape) * (1.6 / np.sqrt(fan_in))).astype(np.float32)
+    if name in ("body_out.fc2.bias", "hands_out.fc2.bias"):      # rot6d heads: O(1) vectors -> well-conditioned rotations
+        return (0.6 * g.standard_normal(shape)).astype(np.float32)
     if "speaker_embedding" in name:
         return (0.2 * g.standard_normal(shape)).astype(np.float32)
     if name == "mask_embedding":
@@ -154,3 +168,14 @@ def make_checkpoint(seed: int = 0, dtype=None):
 
     vq = {p: (build("vq_" + p), dict(VQ_CFGS[p])) for p in VQ_CFGS}
     return build("emage"), dict(EMAGE_CFG), vq
+
+
+def make_lstm_checkpoint(kind: str, seed: int = 0, dtype=None):
+    """Flat reference-layout checkpoint of CamnAudioModel (kind="camn") or DiscoAudioModel ("disco")."""
+    import torch
+    dtype = dtype or torch.float32
+    sd = {}
+    for name, shape in load_manifest()[kind]:
+        arr = synth_tensor(name, shape, seed, kind)
+        sd[name] = torch.from_numpy(arr).to(dtype) if arr is not None else torch.zeros(shape, dtype=torch.long)
+    return sd, dict(LSTM_CFG)

@@ -62,3 +62,26 @@ def test_rotation_round_trip():
     assert (back - aa).abs().max() < 1e-3   # fp32 sqrt(1+-trace) route loses components ~2e-4
     zero = O.rot6d_to_axis_angle(O.axis_angle_to_rot6d(torch.zeros(4, 3)))
     assert zero.abs().max() == 0
+
+
+@pytest.mark.parametrize("kind", ["camn", "disco"])
+def test_lstm_oracle_matches_reference(kind, golden_dir):
+    """CaMN / DisCo (BASELINE configs[2], [3]): oracle/lstm_oracle.py vs outputs of the unmodified reference modules."""
+    from oracle import lstm_oracle as L
+    from oracle.weights import make_lstm_checkpoint
+    sd, cfg = make_lstm_checkpoint(kind, seed=0)
+    g = np.load(os.path.join(golden_dir, f"case_{kind}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"])))
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    fwd = L.camn_forward if kind == "camn" else L.disco_forward
+    with torch.no_grad():
+        a = fwd(sd, cfg, audio, spk, 4, None)
+        b = fwd(sd, cfg, audio, spk, 4, torch.from_numpy(g["seed_motion"]))
+    t = g["motion"].shape[1]
+    np.testing.assert_allclose(a["motion"].reshape(bs, t, -1).numpy(), g["motion"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(b["motion"].reshape(bs, t, -1).numpy(), g["seeded_motion"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(a["motion_axis_angle"].numpy(), g["motion_axis_angle"], atol=1e-3, rtol=0)
+    if kind == "disco":
+        np.testing.assert_allclose(a["audio_fea_c"].numpy(), g["audio_fea_c"], atol=1e-5, rtol=0)
+        np.testing.assert_allclose(a["audio_fea_r"].numpy(), g["audio_fea_r"], atol=1e-5, rtol=0)
