@@ -136,6 +136,21 @@ int pm_pose_compose_f32(const float* face, const float* upper, const float* hand
 int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, float dt,
                         float* trans, int batch, int t, void* stream);
 
+/* ---- CaMN / DisCo (BASELINE configs[2],[3]) ------------------------------------------------------- */
+/* One bidirectional nn.LSTM layer, zero initial state (camn:205-217,264-271; disco:212-216,255).  xproj (batch, t,
+ * ldx >= 8*hidden) holds W_ih x + b_ih + b_hh for both directions (column dir*4H + gate*H + unit, gates i,f,g,o);
+ * whh (2, 4H, H) fp32; y (batch, t, ldy >= 2H) receives [forward h | backward h].  `barrier` = 2 uint32 of scratch.
+ * hidden must be 512.  Persistent cooperative kernel, W_hh resident in shared memory. */
+int pm_lstm_bidir_f32(const float* xproj, long long x_bs, int ldx, const float* whh,
+                      float* y, long long y_bs, int ldy, unsigned int* barrier,
+                      int batch, int t, int hidden, void* stream);
+/* rot6d (rows, n_sel*6) of the selected joints -> axis-angle (rows, 165), zeros at unselected joints: camn:274-277.
+ * slot: device int32[55], position of joint j among the selected ones or -1. */
+int pm_rot6d_to_aa_f32(const float* rot6d, long long rows, int n_sel, const int* slot, float* out, void* stream);
+/* DisCo content mix disco:250-251: out[r,:] = softmax(sel[r,0:2])[0]*c1[r,:] + [1]*c2[r,:] (out row stride ldo) */
+int pm_softmax2_mix_f32(const float* sel, const float* c1, const float* c2, float* out, long long rows, int ch, int ldo,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,9 @@ SIGNATURES = {
     "pm_row_sqnorm_f32": [_p, _i, _i, _p, _p],
     "pm_pose_compose_f32": [_p, _p, _p, _p, _p, _p, _p, _ll, _p],
     "pm_global_trans_f32": [_p, _i, _i, _p, _f, _p, _i, _i, _p],
+    "pm_lstm_bidir_f32": [_p, _ll, _i, _p, _p, _ll, _i, _p, _i, _i, _i, _p],
+    "pm_rot6d_to_aa_f32": [_p, _ll, _i, _p, _p, _p],
+    "pm_softmax2_mix_f32": [_p, _p, _p, _p, _ll, _i, _i, _p],
 }
 
 _lib = None

@@ -122,7 +122,64 @@ __global__ void __launch_bounds__(64) global_trans_kernel(const float* __restric
   }
 }
 
+// rot6d rows of the selected joints -> axis-angle of all 55 joints (zeros elsewhere): rotation_6d_to_axis_angle +
+// recover_from_mask_ts of the CaMN / DisCo heads (camn:274-277).  slot[j] = position of joint j among the selected
+// joints, or -1.
+__global__ void __launch_bounds__(256) rot6d_to_aa_kernel(const float* __restrict__ rot6d, long long rows, int n_sel,
+                                                          const int* __restrict__ slot, float* __restrict__ out) {
+  const long long total = rows * 55;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / 55;
+    const int j = (int)(i % 55);
+    const int sl = slot[j];
+    float aa[3] = {0.f, 0.f, 0.f};
+    if (sl >= 0) {
+      float d[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) d[c] = rot6d[(r * n_sel + sl) * 6 + c];
+      rot6d_to_aa(d, aa);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[r * 165 + j * 3 + c] = aa[c];
+  }
+}
+
+// DisCo content mix (disco:250-251): w = softmax(sel, 2 logits); out = w0 * c1 + w1 * c2, one rounding per op
+__global__ void __launch_bounds__(256) softmax2_mix_kernel(const float* __restrict__ sel, const float* __restrict__ c1,
+                                                           const float* __restrict__ c2, float* __restrict__ out,
+                                                           long long rows, int ch, int ldo) {
+  const long long total = rows * ch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ch;
+    const int c = (int)(i % ch);
+    const float a = sel[2 * r], b = sel[2 * r + 1];
+    const float m = fmaxf(a, b);
+    const float ea = expf(a - m), eb = expf(b - m);
+    const float s = ea + eb;
+    out[r * ldo + c] = (ea / s) * c1[i] + (eb / s) * c2[i];
+  }
+}
+
 }  // namespace
+
+extern "C" int pm_rot6d_to_aa_f32(const float* rot6d, long long rows, int n_sel, const int* slot, float* out, void* stream) {
+  PM_REQUIRE(rot6d && slot && out && rows >= 0 && n_sel > 0 && n_sel <= 55);
+  if (rows == 0) return PM_OK;
+  long long g = (rows * 55 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  rot6d_to_aa_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(rot6d, rows, n_sel, slot, out);
+  PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_softmax2_mix_f32(const float* sel, const float* c1, const float* c2, float* out, long long rows,
+                                   int ch, int ldo, void* stream) {
+  PM_REQUIRE(sel && c1 && c2 && out && rows >= 0 && ch > 0 && ldo >= ch);
+  if (rows == 0) return PM_OK;
+  long long g = (rows * ch + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  softmax2_mix_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(sel, c1, c2, out, rows, ch, ldo);
+  PM_LAUNCH_CHECK();
+}
 
 extern "C" int pm_pose_compose_f32(const float* face, const float* upper, const float* hands, const float* lower,
                                    float* expression, float* axis_angle, float* motion4inf, long long bt,

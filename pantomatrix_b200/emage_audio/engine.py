@@ -261,9 +261,9 @@ class _ConvStack:
 class _WavEncoder:
     """P.py:263-314 with BatchNorm folded; input is a set of (clip, window) waveform slices."""
 
-    def __init__(self, sd, p):
+    def __init__(self, sd, p, blocks=WAV_BLOCKS):
         self.blocks = []
-        for i, (stride, pad, has_ds) in enumerate(WAV_BLOCKS):
+        for i, (stride, pad, has_ds) in enumerate(blocks):
             q = f"{p}.feat_extractor.{i}"
             w1, b1 = _fold_bn(sd, q + ".conv1", q + ".bn1")
             w2, b2 = _fold_bn(sd, q + ".conv2", q + ".bn2")

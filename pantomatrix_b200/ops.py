@@ -350,3 +350,44 @@ def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, ac
           None if prefetch is None else prefetch.data_ptr(),
           0 if prefetch is None else prefetch.numel() * prefetch.element_size(), _stream())
     return out_f, out_p
+
+
+# ------------------------------------------------------------------------------------------------------
+# CaMN / DisCo
+# ------------------------------------------------------------------------------------------------------
+
+
+def lstm_bidir(xproj, whh, barrier, hidden):
+    """One bidirectional LSTM layer.  xproj (batch, t, 8*hidden) = W_ih x + b for [forward | backward] (gates
+    i,f,g,o), whh (2, 4*hidden, hidden).  Returns (batch, t, 2*hidden) = [forward h | backward h]."""
+    _chk(xproj), _chk(whh)
+    assert xproj.is_contiguous() and whh.is_contiguous() and whh.shape == (2, 4 * hidden, hidden)
+    batch, t, w = xproj.shape
+    assert w == 8 * hidden
+    y = torch.empty(batch, t, 2 * hidden, device=xproj.device, dtype=torch.float32)
+    _call("pm_lstm_bidir_f32", xproj.data_ptr(), xproj.stride(0), xproj.stride(1), whh.data_ptr(), y.data_ptr(),
+          y.stride(0), y.stride(1), barrier.data_ptr(), batch, t, hidden, _stream())
+    return y
+
+
+def rot6d_to_aa(rot6d, slot, n_sel):
+    """rot6d (..., n_sel*6) -> axis-angle (..., 165); slot: int32[55] device tensor (position among the selected
+    joints or -1)."""
+    _chk(rot6d)
+    assert rot6d.is_contiguous() and rot6d.shape[-1] == n_sel * 6
+    rows = rot6d.numel() // (n_sel * 6)
+    out = torch.empty(*rot6d.shape[:-1], 165, device=rot6d.device, dtype=torch.float32)
+    _call("pm_rot6d_to_aa_f32", rot6d.data_ptr(), rows, n_sel, slot.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+def softmax2_mix(sel, c1, c2, out=None):
+    """out[..., :] = softmax(sel[..., 0:2])[0] * c1 + [1] * c2 (out may be a column slice of a wider tensor)."""
+    _chk(sel), _chk(c1), _chk(c2)
+    assert sel.is_contiguous() and c1.is_contiguous() and c2.is_contiguous() and sel.shape[-1] == 2
+    ch = c1.shape[-1]
+    rows = c1.numel() // ch
+    if out is None:
+        out = torch.empty_like(c1)
+    _call("pm_softmax2_mix_f32", sel.data_ptr(), c1.data_ptr(), c2.data_ptr(), out.data_ptr(), rows, ch, out.stride(-2), _stream())
+    return out

@@ -186,3 +186,42 @@ def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_c
             y = out
         return y.contiguous() if out is None else y, out_p
     return None, out_p
+
+
+# ---- CaMN / DisCo stand-ins ---------------------------------------------------------------------------
+
+
+def lstm_bidir(xproj, whh, barrier, hidden):
+    bs, T, _ = xproj.shape
+    outs = []
+    for d in range(2):
+        xp, w = xproj[:, :, d * 4 * hidden:(d + 1) * 4 * hidden], whh[d]
+        h, c = torch.zeros(bs, hidden), torch.zeros(bs, hidden)
+        seq = [None] * T
+        for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
+            i, f, g, o = (xp[:, t] + h @ w.t()).split(hidden, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            seq[t] = h
+        outs.append(torch.stack(seq, 1))
+    return torch.cat(outs, 2)
+
+
+def rot6d_to_aa(rot6d, slot, n_sel):
+    from oracle import emage_oracle as O
+    lead = rot6d.shape[:-1]
+    aa = O.rot6d_to_axis_angle(rot6d.reshape(-1, n_sel, 6))
+    full = torch.zeros(aa.shape[0], 55, 3)
+    for j in range(55):
+        if int(slot[j]) >= 0:
+            full[:, j] = aa[:, int(slot[j])]
+    return full.reshape(*lead, 165)
+
+
+def softmax2_mix(sel, c1, c2, out=None):
+    w = torch.softmax(sel, dim=-1)
+    y = w[..., 0:1] * c1 + w[..., 1:2] * c2
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y

@@ -24,3 +24,11 @@ def geodesic_deg(aa_a: torch.Tensor, aa_b: torch.Tensor) -> torch.Tensor:
     rb = quat_to_matrix(axis_angle_to_quat(aa_b.double()))
     tr = (ra.transpose(-1, -2) @ rb).diagonal(dim1=-2, dim2=-1).sum(-1)
     return torch.rad2deg(torch.acos(torch.clamp((tr - 1) / 2, -1, 1)))
+
+
+def build_lstm_product(kind, seed=0, device="cuda"):
+    """CamnAudioModel ("camn") or DiscoAudioModel ("disco") with the synthetic checkpoint."""
+    from oracle.weights import LSTM_CFG
+    from pantomatrix_b200.lstm_audio import CamnAudioConfig, CamnAudioModel, DiscoAudioConfig, DiscoAudioModel
+    cls, ccls = (CamnAudioModel, CamnAudioConfig) if kind == "camn" else (DiscoAudioModel, DiscoAudioConfig)
+    return load_synthetic(cls(ccls(**LSTM_CFG)), seed, kind).to(device).eval()

@@ -20,6 +20,10 @@ def _models():
     for p in ("face", "upper", "hands", "lower"):
         out["vq_" + p] = EmageVQVAEConv(EmageVQVAEConvConfig(**VQ_CFGS[p]))
     out["vq_global"] = EmageVAEConv(EmageVAEConvConfig(**VQ_CFGS["global"]))
+    from oracle.weights import LSTM_CFG
+    from pantomatrix_b200.lstm_audio import CamnAudioConfig, CamnAudioModel, DiscoAudioConfig, DiscoAudioModel
+    out["camn"] = CamnAudioModel(CamnAudioConfig(**LSTM_CFG))
+    out["disco"] = DiscoAudioModel(DiscoAudioConfig(**LSTM_CFG))
     return out
 
 
@@ -50,6 +54,10 @@ def test_export_list_and_shim():
     assert sorted(pkg.__all__) == sorted(names)
     for n in names:
         assert getattr(shim, n) is getattr(pkg, n)
+    import models.camn_audio as camn
+    import models.disco_audio as disco
+    assert sorted(camn.__all__) == ["CamnAudioConfig", "CamnAudioModel", "CamnAudioPreTrainedModel"]
+    assert sorted(disco.__all__) == ["DiscoAudioConfig", "DiscoAudioModel", "DiscoAudioPreTrainedModel"]
 
 
 def test_save_and_from_pretrained_round_trip(tmp_path):

@@ -95,3 +95,23 @@ def test_tensor_core_schedule_host_logic(cpu_product, golden_dir, precision, ato
         np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=atol, rtol=0)
         agree = (lat["cls_" + p].argmax(-1).numpy() == g["idx_cls_" + p]).mean()
         assert agree > (0.999 if precision == "bf16x6" else 0.97), (p, agree)
+
+
+@pytest.mark.parametrize("kind", ["camn", "disco"])
+def test_lstm_models_host_logic(kind, cpu_product, golden_dir):
+    """CaMN / DisCo host side (WavEncoder variant, LSTM weight packing, feature assembly, seed handling) with the
+    kernels emulated, against the reference's golden outputs."""
+    from helpers import build_lstm_product
+    model = build_lstm_product(kind, device="cpu")
+    g = np.load(os.path.join(golden_dir, f"case_{kind}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"])))
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    a = model(audio, spk, seed_frames=4, seed_motion=None)
+    b = model(audio, spk, seed_frames=4, seed_motion=torch.from_numpy(g["seed_motion"]))
+    t = g["motion"].shape[1]
+    assert a["motion"].shape[:2] == (bs, t) and a["motion_axis_angle"].shape == (bs, t, 165)
+    np.testing.assert_allclose(a["motion"].reshape(bs, t, -1).numpy(), g["motion"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(b["motion"].reshape(bs, t, -1).numpy(), g["seeded_motion"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(a["motion_axis_angle"].numpy(), g["motion_axis_angle"], atol=1e-3, rtol=0)
+    assert model(audio, spk, return_axis_angle=False)["motion_axis_angle"] is None

@@ -1,0 +1,121 @@
+"""CaMN / DisCo on the GPU (BASELINE configs[2], [3]): the persistent BiLSTM kernel, the rot6d->axis-angle scatter and
+the DisCo mix kernel against float64 / oracle restatements, and both models end to end against the reference's
+golden outputs and the live oracle at the BASELINE batch sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_lstm_product, geodesic_deg
+from oracle import emage_oracle as O
+from oracle import lstm_oracle as L
+from oracle.weights import make_lstm_checkpoint, synth_audio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pantomatrix_b200 import ops as o
+    return o
+
+
+@pytest.fixture(autouse=True)
+def _exact_engine_by_default():
+    from pantomatrix_b200.emage_audio import engine
+    engine.set_precision("fp32")
+    yield
+    engine.set_precision(engine.DEFAULT_PRECISION)
+
+
+@pytest.mark.parametrize("batch,t", [(64, 149), (5, 45), (70, 9)])
+def test_lstm_layer_matches_fp64(ops, batch, t):
+    H = 512
+    g = torch.Generator().manual_seed(3)
+    xproj = torch.randn(batch, t, 8 * H, generator=g)
+    whh = torch.randn(2, 4 * H, H, generator=g) * (1.2 / H ** 0.5)
+    got = ops.lstm_bidir(xproj.cuda(), whh.cuda(), torch.zeros(2, dtype=torch.int32, device="cuda"), H).cpu()
+    want = []
+    for d in range(2):
+        xp, w = xproj[:, :, d * 4 * H:(d + 1) * 4 * H].double(), whh[d].double()
+        h, c = torch.zeros(batch, H, dtype=torch.double), torch.zeros(batch, H, dtype=torch.double)
+        seq = [None] * t
+        for k in (range(t) if d == 0 else range(t - 1, -1, -1)):
+            i, f, gg, o = (xp[:, k] + h @ w.t()).split(H, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            seq[k] = h
+        want.append(torch.stack(seq, 1))
+    want = torch.cat(want, 2)
+    assert (got.double() - want).abs().max() < 5e-5, (got.double() - want).abs().max()
+
+
+def test_rot6d_to_aa_and_mix_kernels(ops):
+    from pantomatrix_b200.lstm_audio.modeling import MASK_DICT
+    g = torch.Generator().manual_seed(4)
+    mask = MASK_DICT["local_upper"]
+    slot, k = [], 0
+    for m in mask:
+        slot.append(k if m else -1)
+        k += int(m)
+    rot = torch.randn(3, 20, k * 6, generator=g)
+    got = ops.rot6d_to_aa(rot.cuda(), torch.tensor(slot, dtype=torch.int32).cuda(), k).cpu()
+    want = L._to_axis_angle({"joint_mask": "local_upper"}, rot.reshape(3, 20, k, 6), 3, 20)
+    assert geodesic_deg(got.reshape(3, 20, 55, 3), want.reshape(3, 20, 55, 3)).max() < 0.02
+    assert got.reshape(3, 20, 55, 3)[:, :, [0, 1, 2, 22, 23, 24]].abs().max() == 0
+    sel, c1, c2 = torch.randn(3, 20, 2, generator=g), torch.randn(3, 20, 128, generator=g), torch.randn(3, 20, 128, generator=g)
+    w = torch.softmax(sel, -1)
+    got = ops.softmax2_mix(sel.cuda(), c1.cuda(), c2.cuda()).cpu()
+    assert (got - (w[..., 0:1] * c1 + w[..., 1:2] * c2)).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x6"])
+@pytest.mark.parametrize("kind", ["camn", "disco"])
+def test_lstm_models_match_reference_golden(kind, precision, golden_dir):
+    from pantomatrix_b200.emage_audio import engine
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    engine.set_precision(precision)
+    model = build_lstm_product(kind)
+    g = np.load(os.path.join(golden_dir, f"case_{kind}.npz"))
+    bs, n = int(g["bs"]), int(g["n_samples"])
+    audio = torch.from_numpy(synth_audio(bs, n, int(g["audio_seed"]))).cuda()
+    spk = torch.zeros(bs, 1, dtype=torch.long, device="cuda")
+    a = model(audio, spk, seed_frames=4, seed_motion=None)
+    b = model(audio, spk, seed_frames=4, seed_motion=torch.from_numpy(g["seed_motion"]).cuda())
+    t = g["motion"].shape[1]
+    np.testing.assert_allclose(a["motion"].reshape(bs, t, -1).cpu().numpy(), g["motion"], atol=1e-3, rtol=0)
+    np.testing.assert_allclose(b["motion"].reshape(bs, t, -1).cpu().numpy(), g["seeded_motion"], atol=1e-3, rtol=0)
+    geo = geodesic_deg(a["motion_axis_angle"].cpu().reshape(bs, t, 55, 3), torch.from_numpy(g["motion_axis_angle"]).reshape(bs, t, 55, 3))
+    assert geo.max() < 0.5 and geo.median() < 1e-2, (geo.max().item(), geo.median().item())
+    if kind == "disco":
+        np.testing.assert_allclose(a["audio_fea_c"].cpu().numpy(), g["audio_fea_c"], atol=1e-3, rtol=0)
+
+
+@pytest.mark.parametrize("kind,bs", [("camn", 64), ("disco", 32)])
+def test_lstm_models_at_baseline_batch(kind, bs):
+    """BASELINE configs[2] (CaMN, batch 64) and [3] (DisCo, batch 32): 10 s clips -> 149 frames @ 15 fps, vs the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.set_num_threads(min(16, os.cpu_count()))
+    model = build_lstm_product(kind)
+    sd, cfg = make_lstm_checkpoint(kind, 0)
+    audio = torch.from_numpy(synth_audio(bs, 160000, 99))
+    spk = torch.zeros(bs, 1, dtype=torch.long)
+    got = model(audio.cuda(), spk.cuda())
+    assert got["motion_axis_angle"].shape == (bs, 149, 165)
+    with torch.no_grad():
+        want = (L.camn_forward if kind == "camn" else L.disco_forward)(sd, cfg, audio, spk)
+    err = (got["motion"].reshape(bs, 149, -1).cpu() - want["motion"].reshape(bs, 149, -1)).abs().max().item()
+    assert err < 1e-3, err
+    raw = got["motion"].reshape(bs, 149, 43, 6).cpu().double()
+    a1, a2 = raw[..., :3], raw[..., 3:]
+    b1 = a1 / a1.norm(dim=-1, keepdim=True)
+    kappa = 1.0 / torch.minimum(a1.norm(dim=-1), (a2 - (b1 * a2).sum(-1, keepdim=True) * b1).norm(dim=-1))
+    sel = [j for j in range(55) if (j in (3, 6, 9) or 12 <= j <= 21 or j >= 25)]
+    geo = torch.deg2rad(geodesic_deg(got["motion_axis_angle"].cpu().reshape(bs, 149, 55, 3), want["motion_axis_angle"].reshape(bs, 149, 55, 3)))[:, :, sel]
+    allowed = torch.maximum(torch.full_like(kappa, 1e-3), 1e-4 * kappa)
+    assert bool((geo <= allowed).all()), float((geo - allowed).max())

@@ -45,6 +45,9 @@ CASES = [
     (5, 700, 64, 64, 15, 7),           # WavEncoder conv2 (BN = 64 tile)
     (4, 205, 128, 128, 15, 7),
     (2, 11, 256, 256, 3, 1),           # 11-frame tail window
+    (4, 700, 32, 32, 15, 7),           # CaMN / DisCo WavEncoder: cin < one 64-channel k-block (TMA box wider than the tensor)
+    (2, 45, 512, 78, 1, 0),            # CaMN body head (ragged cout)
+    (2, 45, 403, 4096, 1, 0),          # LSTM input projection, both directions (ragged cin)
 ]
 
 
@@ -85,9 +88,10 @@ def test_partial_activation_and_column_slices(ops):
     _check(got2, F.linear(got[:, :, 64:].double(), w2[0].double()), 3, float(got2.abs().max()))
 
 
-def test_strided_conv_as_reshaped_stride1(ops):
+@pytest.mark.parametrize("C,cout", [(64, 64), (32, 64)])
+def test_strided_conv_as_reshaped_stride1(ops, C, cout):
     """k=15 stride-6 conv == 3-tap stride-1 conv over the (L/6, 6*C) view with zero-padded taps."""
-    b, L, C, cout, s = 3, 745, 64, 64, 6
+    b, L, s = 3, 745, 6
     x = _rand(b, L, C, seed=8)
     w = _rand(cout, C, 15, seed=9, scale=1 / math.sqrt(C * 15))
     want = F.conv1d(x.double().transpose(1, 2), w.double(), stride=s).transpose(1, 2)
