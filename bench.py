@@ -37,6 +37,7 @@ DTYPES = {"fp32": "f32", "bf16x6": "bf16x6 (split-bf16 operands, f32 accumulate)
           "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)", "bf16": "bf16"}
 ENGINES = {"fp32": "fp32 SIMT tap-GEMM", "bf16x6": "tcgen05 tap-GEMM, 6 bf16 products per fp32 product",
            "bf16x3": "tcgen05 tap-GEMM, 3 bf16 products per fp32 product", "bf16": "tcgen05 tap-GEMM, plain bf16"}
+NCU_TRAFFIC_BYTES = {"bf16x6": 26.4e6}          # per launch, see roofline.traffic_note
 MMA_PER_PRODUCT = {"fp32": 0, "bf16": 1, "bf16x3": 3, "bf16x6": 6}
 METRIC = "motion_frames_per_sec"
 UNIT = "frames/s"
@@ -317,7 +318,10 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "tap-GEMM (conv1d + linear), all launches of one step",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "launches_per_step": gl, "kernel_ms_per_step": gms,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.precision), "launches_per_step": gl, "kernel_ms_per_step": gms,
+                         "traffic_note": "dram__bytes_read+write of one representative launch (M=2048,N=768,K=768 trunk GEMM, "
+                                         "grid 16x6) from the committed ncu --set full capture profiles/ncu_full_r1_final.md "
+                                         "(cold caches); algorithmic bytes of that launch: 19.2 MB in bf16x6",
                          "mma_per_fp32_product": MMA_PER_PRODUCT[args.precision],
                          "tensor_pipe_frac": achieved * MMA_PER_PRODUCT[args.precision] / peak,
                          "note": "achieved = algorithmic FLOP (2*rows*cout*cin*taps) / CUDA-event time of each launch, "
