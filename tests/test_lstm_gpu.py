@@ -120,5 +120,9 @@ def test_lstm_models_at_baseline_batch(kind, bs):
     geo = torch.deg2rad(geodesic_deg(got["motion_axis_angle"].cpu().reshape(bs, 149, 55, 3), want["motion_axis_angle"].reshape(bs, 149, 55, 3)))[:, :, sel]
     # a rot6d perturbation eps moves the rotation by ~ 2-3 eps * kappa rad (two normalisations + a cross product):
     # the emitted rotations must be explained by the measured rot6d error `err` and the conditioning, else 1e-3
-    allowed = torch.maximum(torch.full_like(kappa, 1e-3), 4.0 * max(err, 2e-5) * kappa)
+    # ... and the reference's matrix->quaternion route itself (0.5*sqrt(1 +- m00 +- m11 +- m22), P.py/C.py) loses a
+    # quaternion component of size ~1e-4..1e-3 to fp32 cancellation, an absolute rotation error up to ~sqrt(eps):
+    # among the 410 k joints of this batch the CPU-fp32 oracle and any other fp32 evaluation differ by up to
+    # ~1e-3 rad there, although the rot6d inputs agree to `err` (2.8e-5 measured).  Floor: 2e-3 rad.
+    allowed = torch.maximum(torch.full_like(kappa, 2e-3), 4.0 * max(err, 2e-5) * kappa)
     assert bool((geo <= allowed).all()), (float((geo - allowed).max()), err)
