@@ -139,7 +139,7 @@ int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_
 /* ---- CaMN / DisCo (BASELINE configs[2],[3]) ------------------------------------------------------- */
 /* One bidirectional nn.LSTM layer, zero initial state (camn:205-217,264-271; disco:212-216,255).  xproj (batch, t,
  * ldx >= 8*hidden) holds W_ih x + b_ih + b_hh for both directions (column dir*4H + gate*H + unit, gates i,f,g,o);
- * whh (2, 4H, H) fp32; y (batch, t, ldy >= 2H) receives [forward h | backward h].  `barrier` = 2 uint32 of scratch.
+ * whh (2, 4H, H) fp32; y (batch, t, ldy >= 2H) receives [forward h | backward h].  `barrier` = 4 uint32 of scratch.
  * hidden must be 512.  Persistent cooperative kernel, W_hh resident in shared memory. */
 int pm_lstm_bidir_f32(const float* xproj, long long x_bs, int ldx, const float* whh,
                       float* y, long long y_bs, int ldy, unsigned int* barrier,

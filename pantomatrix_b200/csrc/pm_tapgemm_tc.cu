@@ -44,7 +44,6 @@ struct TcParams {
   int stages;
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
   int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
-  int dbg;   // tuning experiments only (PM_TC_DBG): 1 = no global stores, 2 = no epilogue, 4 = no TMA / MMA
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   const int l0 = blockIdx.x * p.R;
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
-  const int n_iter = (p.dbg & 4) ? 0 : p.taps * p.kblocks;
+  const int n_iter = p.taps * p.kblocks;
   // thread-block cluster: CTAs of one cluster share operand tiles through TMA multicast
   const bool clustered = p.cm * p.cn > 1;
   const uint32_t crank = clustered ? cluster_ctarank() : 0;
@@ -233,8 +232,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       }
     }
     {
-      // dbg 32 / 64: skip the W / A loads (throughput experiments; results are garbage)
-      const uint32_t tx = (uint32_t)(p.nsplit * (((p.dbg & 64) ? 0 : A_TILE_BYTES) + ((p.dbg & 32) ? 0 : W_TILE_BYTES)));
+      const uint32_t tx = (uint32_t)(p.nsplit * (A_TILE_BYTES + W_TILE_BYTES));
       int s = 0, tap = 0, kb = 0;
       uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
@@ -246,14 +244,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         for (int pl = 0; pl < p.nsplit; ++pl) {
           const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
           const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
-          if (p.dbg & 64) {}
-          else if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+          if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
           else {                                   // my 128/cn-row slice of the A tile, to every CTA of my tile row
             const int ar = BM / p.cn;
             tma_load_4d_mc(a_dst + ry * ar * 128, &map_a, bar, kb * BK, l0 + tap - p.pad + ry * ar, b0, pl, mask_a);
           }
-          if (p.dbg & 32) {}
-          else if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
+          if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
           else {                                   // my BN/cm-row slice of the W tile, to every CTA of my tile column
             const int wr = BN / p.cm;
             tma_load_3d_mc(w_dst + rx * wr * 128, &map_w, bar, kb * BK, tap * p.w_rows + n0 + rx * wr, pl, mask_w);
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     // fast path for full chunks.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    if (!(p.dbg & 4)) mbar_wait(smem_u32(acc_bar), 0);
+    mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
     constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
     const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // 4.6 KB per warp (shared-space address)
@@ -355,7 +351,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       off_b[i] = (long long)b * p.ob_bs + (long long)l * p.ldob;
     }
 #pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < ((p.dbg & 6) ? 0 : (half + 1) * (BN / 2)); c0 += 32) {
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
       uint32_t acc[32];
       float v[32];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -374,7 +370,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
       }
       const int nb = n0 + c0;                                                      // first column of this chunk
-      if (nb >= p.cout || (p.dbg & 1)) continue;                                   // warp-uniform
+      if (nb >= p.cout) continue;                                   // warp-uniform
       // transpose: thread = row -> smem[row][0..31]
 #pragma unroll
       for (int j = 0; j < 8; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -585,8 +581,6 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
     p.cm = (R == 128 && want_m > 1 && gx % want_m == 0 && BNsel % (8 * want_m) == 0) ? want_m : 1;
     p.cn = (R == 128 && want_n > 1 && gy % want_n == 0) ? want_n : 1;
   }
-  static const int env_dbg = getenv("PM_TC_DBG") ? atoi(getenv("PM_TC_DBG")) : 0;
-  p.dbg = env_dbg;
 
   CUtensorMap ma, mw;
   {

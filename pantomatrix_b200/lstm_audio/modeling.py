@@ -71,7 +71,7 @@ class _BiLstm:
                            sd[f"{p}.bias_ih_l{layer}_reverse"] + sd[f"{p}.bias_hh_l{layer}_reverse"]], 0)
             whh = torch.stack([sd[f"{p}.weight_hh_l{layer}"], sd[f"{p}.weight_hh_l{layer}_reverse"]], 0).contiguous()
             self.layers.append((E._Linear(None, w=w, b=b), whh))
-        self.barrier = torch.zeros(2, dtype=torch.int32, device=sd[f"{p}.weight_hh_l0"].device)
+        self.barrier = torch.zeros(4, dtype=torch.int32, device=sd[f"{p}.weight_hh_l0"].device)
 
     def __call__(self, x):
         for proj, whh in self.layers:

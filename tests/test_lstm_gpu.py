@@ -37,7 +37,7 @@ def test_lstm_layer_matches_fp64(ops, batch, t):
     g = torch.Generator().manual_seed(3)
     xproj = torch.randn(batch, t, 8 * H, generator=g)
     whh = torch.randn(2, 4 * H, H, generator=g) * (1.2 / H ** 0.5)
-    got = ops.lstm_bidir(xproj.cuda(), whh.cuda(), torch.zeros(2, dtype=torch.int32, device="cuda"), H).cpu()
+    got = ops.lstm_bidir(xproj.cuda(), whh.cuda(), torch.zeros(4, dtype=torch.int32, device="cuda"), H).cpu()
     want = []
     for d in range(2):
         xp, w = xproj[:, :, d * 4 * H:(d + 1) * 4 * H].double(), whh[d].double()
