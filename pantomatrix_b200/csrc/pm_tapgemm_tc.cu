@@ -44,6 +44,7 @@ struct TcParams {
   int stages;
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
   int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
+  int pdl;      // launched with programmatic stream serialization: prologue overlaps the previous kernel's tail
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -213,6 +214,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   if (clustered) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.pdl) {
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran
+    // while the previous kernel on the stream was still draining.  Let the NEXT kernel start its own prologue as
+    // soon as SMs free up, then wait until the previous kernel's memory is complete and visible before any thread
+    // touches activations (TMA loads, residual reads) or writes outputs.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -505,19 +514,31 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (p.cm * p.cn > 1) {
+  // PM_TC_PDL=1: programmatic dependent launch (see the kernel prologue).
+  static const bool env_pdl = getenv("PM_TC_PDL") && atoi(getenv("PM_TC_PDL")) != 0;
+  p.pdl = env_pdl ? 1 : 0;
+  if (p.cm * p.cn > 1 || p.pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.cm;
-    attr[0].val.clusterDim.y = p.cn;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (p.cm * p.cn > 1) {
+      attr[n].id = cudaLaunchAttributeClusterDimension;
+      attr[n].val.clusterDim.x = p.cm;
+      attr[n].val.clusterDim.y = p.cn;
+      attr[n].val.clusterDim.z = 1;
+      ++n;
+    }
+    if (p.pdl) {
+      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[n].val.programmaticStreamSerializationAllowed = 1;
+      ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n;
     cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN>, ma, mw, p);
     return e == cudaSuccess ? PM_OK : (int)e;
   }
