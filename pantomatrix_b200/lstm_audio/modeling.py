@@ -10,13 +10,13 @@ axis-angle + joint scatter in pm_rot6d_to_aa_f32.  No CPU / eager fallback.
 from __future__ import annotations
 
 import torch
-from transformers import PretrainedConfig, PreTrainedModel
+from transformers import PretrainedConfig
 
 from .. import ops
 from ..emage_audio import engine as E
 from ..emage_audio.configuration import _splat
 from ..emage_audio import modeling as _M
-from ..emage_audio.modeling import _bn, _conv, _EngineOwner, _lin, _materialise, _mlp, _plain_state
+from ..emage_audio.modeling import _bn, _conv, _EngineOwner, _materialise, _mlp, _plain_state
 
 # (cin, cout, stride, first padding) of the six BasicBlocks, C.py:138-145; a block has a downsample branch iff
 # stride != 1 or cin != cout (C.py:113-118)
