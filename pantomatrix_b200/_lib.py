@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpm_emage.so")
+# PM_EMAGE_LIB: an instrumented / tuning build of the same sources (pantomatrix_b200.build --variant), tools only
+LIB_PATH = os.environ.get("PM_EMAGE_LIB") or os.path.join(_HERE, "libpm_emage.so")
 
 _p = C.c_void_p
 _i = C.c_int

@@ -1,6 +1,7 @@
 """In-tree nvcc build of libpm_emage.so (sm_100a only; the built .so travels to the GPU box).
 
     python -m pantomatrix_b200.build [--force]
+    python -m pantomatrix_b200.build --variant NAME -DMACRO[=V] ...   # instrumented / tuning build, see build_variant()
 """
 from __future__ import annotations
 
@@ -70,5 +71,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Side build of the same sources with extra -D macros (e.g. PM_TC_TIMING: in-kernel clock stamps) into
+    csrc/_build/variants/libpm_emage_<name>.so.  Never loaded by default: tools select it with PM_EMAGE_LIB=<path>."""
+    vdir = os.path.join(OBJ, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = _nvcc()
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(vdir, src[:-3] + ".o")
+        cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), *defines, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode:
+            print(f"--- {src}\n{out}", file=sys.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+    lib = os.path.join(OBJ, "variants", f"libpm_emage_{name}.so")
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", lib, *objs])
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        print(build_variant(sys.argv[sys.argv.index("--variant") + 1], [a for a in sys.argv if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

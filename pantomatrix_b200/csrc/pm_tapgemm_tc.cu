@@ -47,6 +47,20 @@ struct TcParams {
   int pdl;      // launched with programmatic stream serialization: prologue overlaps the previous kernel's tail
 };
 
+// Instrumented build only (-DPM_TC_TIMING, tools/gemm_timeline.py): per-CTA clock64 stamps of the kernel's phases.
+#ifdef PM_TC_TIMING
+__device__ unsigned long long pm_tc_stamps[4096 * 8];
+#define PM_STAMP(i)                                                                                              \
+  do {                                                                                                           \
+    if ((threadIdx.x & 31) == 0) {                                                                               \
+      const unsigned cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                      \
+      if (cta_ < 4096) pm_tc_stamps[cta_ * 8 + (i)] = (unsigned long long)clock64();                             \
+    }                                                                                                            \
+  } while (0)
+#else
+#define PM_STAMP(i) do {} while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) PM_STAMP(0);                                   // kernel entry
   const int l0 = blockIdx.x * p.R;
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
@@ -214,6 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   if (clustered) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) PM_STAMP(1);                                   // prologue done (barriers, TMEM, descriptors)
   if (p.pdl) {
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran
     // while the previous kernel on the stream was still draining.  Let the NEXT kernel start its own prologue as
@@ -287,6 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       for (int it = 0; it < n_iter; ++it) {
         mbar_wait_fast(smem_u32(&full_bar[s]), ph);               // whole warp waits (uniform control flow)
         tc_fence_after();
+        if (it == 0) PM_STAMP(2);                                 // first operand stage landed
         if (elect_one()) {
         const uint32_t a_base = tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
         const uint64_t a0 = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFFu);                       // A plane 0, k = 0
@@ -324,6 +341,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       if (n_iter > 0 && elect_one()) tc_commit(smem_u32(acc_bar));      // accumulator complete
+      PM_STAMP(3);                                                // all MMAs issued
     }
   } else {
     // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
@@ -337,6 +355,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     const int half = (warp - 2) >> 2;
     mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
+    if (warp == 2) PM_STAMP(4);                                   // accumulators complete
     constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
     const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // 4.6 KB per warp (shared-space address)
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;              // this lane's row-in-group / first column of its float4
@@ -396,12 +415,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       // identity == leaky with slope 1: one branch-free formula for none / relu / leaky / partial activation
       const float s0 = n < p.act_cols ? act_slope : 1.f, s1 = n + 1 < p.act_cols ? act_slope : 1.f;
       const float s2 = n + 2 < p.act_cols ? act_slope : 1.f, s3 = n + 3 < p.act_cols ? act_slope : 1.f;
+      if (fast) {
+        // Hot path, kept contiguous and small: the ragged path below is rolled and placed after it, so the
+        // instructions actually executed do not straddle 200+ KB of cold unrolled code (in-kernel clock stamps,
+        // profiles/gemm_timeline_r1.txt: the epilogue was instruction-fetch bound).
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (!((row_ok >> i) & 1u)) continue;
-        float4 x = lds128(stage + ((4 * i + sub_r) * ST + c4) * 4);
-        x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-        if (fast) {
+        for (int i = 0; i < 8; ++i) {
+          if (!((row_ok >> i) & 1u)) continue;
+          float4 x = lds128(stage + ((4 * i + sub_r) * ST + c4) * 4);
+          x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
           if (p.residual) {
             const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
@@ -415,17 +437,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             const PmPlanes P{p.out_bf16 + off_b[i], p.ob_ps, p.ldob, p.out_nsplit};
             pm_store_planes4(P, 0, n, x);
           }
-        } else if (n < p.cout) {                                                   // ragged / unaligned tail: per element
-          float xs[4] = {x.x, x.y, x.z, x.w};
-          const float ss[4] = {s0, s1, s2, s3};
-          const PmPlanes P{p.out_bf16 ? p.out_bf16 + off_b[i] : nullptr, p.ob_ps, p.ldob, p.out_nsplit};
-#pragma unroll
+        }
+      } else if (n < p.cout) {
+        // ragged / unaligned tail: per element, rolled (offsets recomputed so the arrays above stay in registers)
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const int rt = q * 32 + 4 * i + sub_r;
+          const int b = b0 + (rt >> r_shift), l = l0 + (rt & (p.R - 1));
+          if (b >= p.batch || l >= p.rows_out) continue;
+          const long long of = (long long)b * p.o_bs + (long long)l * p.ldo;
+          const long long orr = (long long)b * p.r_bs + (long long)l * p.ldr;
+          const PmPlanes P{p.out_bf16 ? p.out_bf16 + (long long)b * p.ob_bs + (long long)l * p.ldob : nullptr,
+                           p.ob_ps, p.ldob, p.out_nsplit};
+          const uint32_t src = stage + ((4 * i + sub_r) * ST + c4) * 4;
+#pragma unroll 1
           for (int k = 0; k < 4; ++k) {
             if (n + k >= p.cout) break;
-            float y = xs[k];
-            if (p.residual) y += p.residual[off_r[i] + n + k];
-            y = fmaxf(y, 0.f) + ss[k] * fminf(y, 0.f);
-            if (p.out_f32) p.out_f32[off_f[i] + n + k] = y;
+            float y;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(src + 4 * k) : "memory");
+            y += k == 0 ? bias4.x : (k == 1 ? bias4.y : (k == 2 ? bias4.z : bias4.w));
+            if (p.residual) y += p.residual[orr + n + k];
+            y = fmaxf(y, 0.f) + (k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) * fminf(y, 0.f);
+            if (p.out_f32) p.out_f32[of + n + k] = y;
             if (P.ptr) pm_store_planes(P, 0, n + k, y);
           }
         }
@@ -433,9 +466,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     }
   }
 
+  if (warp == 2) PM_STAMP(5);                                     // this warp's share of the epilogue issued
   // teardown: everyone done with TMEM before the owning warp frees it
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) PM_STAMP(6);                                     // all warps done
   if (clustered) cluster_sync_all();        // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -624,6 +659,22 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream);
   return launch<128>(ma, mw, p, grid, (cudaStream_t)stream);
 }
+
+#ifdef PM_TC_TIMING
+extern "C" int pm_tc_timing_reset() {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  void* d = nullptr;
+  e = cudaGetSymbolAddress(&d, pm_tc_stamps);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(d, 0, sizeof(unsigned long long) * 4096 * 8);
+}
+extern "C" int pm_tc_timing_read(unsigned long long* host) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(host, pm_tc_stamps, sizeof(unsigned long long) * 4096 * 8);
+}
+#endif
 
 extern "C" int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,
                              uint16_t* out, long long o_ps, long long o_bs, int ldo, int nsplit, void* stream) {
