@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cstring>
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
 
@@ -171,6 +172,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
 // ---------------------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   // the accumulator's exponent on every MMA, a biased error ~2^-25 |acc| per instruction; keeping the 2^-8-scaled
   // cross terms apart and halving the chain length of the main sums brings the result back to fp32-FMA quality.
   // The epilogue adds the three in fp32.
-  constexpr int TMEM_COLS = BN == 64 ? 256 : 512;   // 3 * BN rounded up to a power of two
+  constexpr int TMEM_COLS = BN == 64 ? 256 : 512;   // 3 accumulators rounded up to a power of two
+  constexpr int ACC = BN == 96 ? 128 : BN;          // column stride between the accumulators
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][nsplit A tiles][nsplit W tiles] (1024-aligned), then barriers
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     {
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t tiles_u32 = smem_u32(tiles);
-      const uint32_t d_corr = tmem_base + 2 * BN;
+      const uint32_t d_corr = tmem_base + 2 * ACC;
       uint32_t first_main0 = 1, first_main1 = 1, first_corr = 1;     // 1 until the accumulator has been written once
       int s = 0;
       uint32_t ph = 0;
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         const uint64_t w0 = desc_hi | (uint64_t)(((a_base + p.nsplit * A_TILE_BYTES) >> 4) & 0x3FFFu);
         constexpr uint64_t A_PL = A_TILE_BYTES >> 4, W_PL = W_TILE_BYTES >> 4, K_ST = (UMMA_K * 2) >> 4;   // descriptor units
         const bool odd = it & 1;
-        const uint32_t d_main = tmem_base + (odd ? BN : 0);
+        const uint32_t d_main = tmem_base + (odd ? ACC : 0);
         // cross products first (small -> large), into the correction accumulator
         if (p.nsplit == 3) {
 #pragma unroll
@@ -356,9 +370,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
     if (warp == 2) PM_STAMP(4);                                   // accumulators complete
-    constexpr int ST = 36;                                         // staging row stride (floats): 16B aligned, conflict-free
-    const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // 4.6 KB per warp (shared-space address)
-    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;              // this lane's row-in-group / first column of its float4
+    // Column chunk per tcgen05.ld: 32, or 16 for the 96-column tile (each warp group owns 48 columns).
+    constexpr int CW = BN == 96 ? 16 : 32;
+    constexpr int LPR = CW / 4;                                    // lanes per staged row (one float4 each)
+    constexpr int RPI = 32 / LPR;                                  // rows written per warp-wide store
+    constexpr int NIT = 32 / RPI;                                  // store rounds per chunk
+    constexpr int ST = CW + 4;                                     // staging row stride (floats): 16B aligned, conflict-free
+    const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // <= 4.6 KB per warp (shared-space address)
+    const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;           // this lane's row-in-group / first column of its float4
     const int r_shift = 31 - __clz(p.R);                           // R is a power of two
     const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
     const bool vec_r = p.residual && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
@@ -366,12 +385,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
                        ((p.ob_bs & 3) == 0) && ((p.ob_ps & 3) == 0);
     const bool all_vec = (!p.out_f32 || vec_f) && (!p.residual || vec_r) && (!p.out_bf16 || vec_b);
     const float act_slope = p.act == PM_ACT_NONE ? 1.f : (p.act == PM_ACT_RELU ? 0.f : p.slope);
-    // rows this lane stores (8 per chunk): offsets are chunk-invariant
-    long long off_f[8], off_r[8], off_b[8];
+    // rows this lane stores (NIT per chunk): offsets are chunk-invariant
+    long long off_f[NIT], off_r[NIT], off_b[NIT];
     uint32_t row_ok = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rt = q * 32 + 4 * i + sub_r;
+    for (int i = 0; i < NIT; ++i) {
+      const int rt = q * 32 + RPI * i + sub_r;
       const int b = b0 + (rt >> r_shift), l = l0 + (rt & (p.R - 1));
       if (b < p.batch && l < p.rows_out) row_ok |= 1u << i;
       off_f[i] = (long long)b * p.o_bs + (long long)l * p.ldo;
@@ -379,32 +398,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       off_b[i] = (long long)b * p.ob_bs + (long long)l * p.ldob;
     }
 #pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-      uint32_t acc[32];
-      float v[32];
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += CW) {
+      uint32_t acc[CW];
+      float v[CW];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       __syncwarp();                                                                // .sync.aligned: whole warp converged
-      tmem_ld32(lane_col, acc);
+      tmem_ld(lane_col, acc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(acc[j]);
       if (n_iter > 1) {                                                            // second main accumulator in use
-        tmem_ld32(lane_col + BN, acc);
+        tmem_ld(lane_col + ACC, acc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+        for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(acc[j]);
       }
       if (p.nsplit > 1) {                                                          // cross-product accumulator
-        tmem_ld32(lane_col + 2 * BN, acc);
+        tmem_ld(lane_col + 2 * ACC, acc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(acc[j]);
+        for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(acc[j]);
       }
       const int nb = n0 + c0;                                                      // first column of this chunk
       if (nb >= p.cout) continue;                                   // warp-uniform
-      // transpose: thread = row -> smem[row][0..31]
+      // transpose: thread = row -> smem[row][0..CW)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < CW / 4; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int n = nb + c4;                                                       // this lane's first column
-      const bool fast = all_vec && nb + 32 <= p.cout;                              // warp-uniform: whole chunk inside cout
+      const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) {
         if (n < p.cout) bias4.x = __ldg(p.bias + n);
@@ -420,9 +439,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         // instructions actually executed do not straddle 200+ KB of cold unrolled code (in-kernel clock stamps,
         // profiles/gemm_timeline_r1.txt: the epilogue was instruction-fetch bound).
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NIT; ++i) {
           if (!((row_ok >> i) & 1u)) continue;
-          float4 x = lds128(stage + ((4 * i + sub_r) * ST + c4) * 4);
+          float4 x = lds128(stage + ((RPI * i + sub_r) * ST + c4) * 4);
           x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
           if (p.residual) {
             const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
@@ -441,15 +460,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       } else if (n < p.cout) {
         // ragged / unaligned tail: per element, rolled (offsets recomputed so the arrays above stay in registers)
 #pragma unroll 1
-        for (int i = 0; i < 8; ++i) {
-          const int rt = q * 32 + 4 * i + sub_r;
+        for (int i = 0; i < NIT; ++i) {
+          const int rt = q * 32 + RPI * i + sub_r;
           const int b = b0 + (rt >> r_shift), l = l0 + (rt & (p.R - 1));
           if (b >= p.batch || l >= p.rows_out) continue;
           const long long of = (long long)b * p.o_bs + (long long)l * p.ldo;
           const long long orr = (long long)b * p.r_bs + (long long)l * p.ldr;
           const PmPlanes P{p.out_bf16 ? p.out_bf16 + (long long)b * p.ob_bs + (long long)l * p.ldob : nullptr,
                            p.ob_ps, p.ldob, p.out_nsplit};
-          const uint32_t src = stage + ((4 * i + sub_r) * ST + c4) * 4;
+          const uint32_t src = stage + ((RPI * i + sub_r) * ST + c4) * 4;
 #pragma unroll 1
           for (int k = 0; k < 4; ++k) {
             if (n + k >= p.cout) break;
@@ -612,6 +631,14 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   int BNsel = cout <= 64 ? 64 : 128;
   static const int env_bn = getenv("PM_TC_BN") ? atoi(getenv("PM_TC_BN")) : 0;      // tuning override: 64 | 128
   if (BNsel == 128 && env_bn == 64) BNsel = 64;   // measured slower (profiles/gemm_microbench_r1.md): off by default
+  // 96-column tiles: 128 CTAs instead of 96 for the M = 2048, N = 768 trunk GEMMs (N = 1536: 256 instead of 192).
+  // Opt-in (PM_TC_BN=96) until it has been measured; only where it lowers waves x tile width.
+  if (BNsel == 128 && env_bn == 96 && w_rows % 96 == 0) {
+    const long long mt = (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB);
+    const long long w128 = (mt * pm_cdiv(cout, 128) + 147) / 148 * 128, w96 = (mt * pm_cdiv(cout, 96) + 147) / 148 * 96;
+    static const bool force96 = getenv("PM_TC_BN") && strchr(getenv("PM_TC_BN"), 'f');   // "96f": wherever legal (tests)
+    if (w96 < w128 || force96) BNsel = 96;
+  }
   PM_REQUIRE(w_rows % BNsel == 0);
 
   TcParams p;
@@ -657,6 +684,7 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
   if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream);
+  if (BNsel == 96) return launch<96>(ma, mw, p, grid, (cudaStream_t)stream);
   return launch<128>(ma, mw, p, grid, (cudaStream_t)stream);
 }
 

@@ -103,3 +103,17 @@ def test_strided_conv_as_reshaped_stride1(ops, C, cout):
     rows_v = -(-L // s)
     got, _ = ops.tapgemm_tc(a, ops.PackedW(wp, 3), None, rows_out=want.shape[1], a_view=(rows_v, s * C, s * C))
     _check(got, want, 3, float(want.abs().max()))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PM_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in: 96-column tiles are not part of the default path yet (PM_TEST_EXPERIMENTAL=1)")
+def test_bn96_tiles_in_subprocess():
+    """The same parity cases with PM_TC_BN=96f (96-column tiles wherever the packed weights allow).  The knob is read
+    once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PM_TC_BN="96f", PM_TEST_EXPERIMENTAL="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
