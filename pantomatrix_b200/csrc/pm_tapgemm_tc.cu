@@ -367,9 +367,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     // fast path for full chunks.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+#ifndef PM_TC_EPI_PREFETCH
     mbar_wait(smem_u32(acc_bar), 0);
     tc_fence_after();
     if (warp == 2) PM_STAMP(4);                                   // accumulators complete
+#endif
     // Column chunk per tcgen05.ld: 32, or 16 for the 96-column tile (each warp group owns 48 columns).
     constexpr int CW = BN == 96 ? 16 : 32;
     constexpr int LPR = CW / 4;                                    // lanes per staged row (one float4 each)
@@ -402,6 +404,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       uint32_t acc[CW];
       float v[CW];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+#ifdef PM_TC_EPI_PREFETCH
+      // Variant (unmeasured, -DPM_TC_EPI_PREFETCH): everything that does not depend on the accumulators - row
+      // offsets above, this chunk's bias and residual loads - is issued BEFORE the accumulator wait / TMEM loads,
+      // so their global latency overlaps the tail of the mainloop instead of sitting in the epilogue.
+      const int nb = n0 + c0;                                                      // first column of this chunk
+      const int n = nb + c4;                                                       // this lane's first column
+      const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) {
+        if (n < p.cout) bias4.x = __ldg(p.bias + n);
+        if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
+        if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
+        if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
+      }
+      float4 rres[NIT];
+      if (fast && p.residual) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i)
+          rres[i] = ((row_ok >> i) & 1u) ? *reinterpret_cast<const float4*>(p.residual + off_r[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (c0 == half * (BN / 2)) {
+        mbar_wait(smem_u32(acc_bar), 0);
+        tc_fence_after();
+        if (warp == 2) PM_STAMP(4);                                 // accumulators complete
+      }
+#endif
       __syncwarp();                                                                // .sync.aligned: whole warp converged
       tmem_ld(lane_col, acc);
 #pragma unroll
@@ -416,12 +444,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(acc[j]);
       }
+#ifndef PM_TC_EPI_PREFETCH
       const int nb = n0 + c0;                                                      // first column of this chunk
+#endif
       if (nb >= p.cout) continue;                                   // warp-uniform
       // transpose: thread = row -> smem[row][0..CW)
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
+#ifndef PM_TC_EPI_PREFETCH
       const int n = nb + c4;                                                       // this lane's first column
       const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -431,6 +462,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
         if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
       }
+#endif
       // identity == leaky with slope 1: one branch-free formula for none / relu / leaky / partial activation
       const float s0 = n < p.act_cols ? act_slope : 1.f, s1 = n + 1 < p.act_cols ? act_slope : 1.f;
       const float s2 = n + 2 < p.act_cols ? act_slope : 1.f, s3 = n + 3 < p.act_cols ? act_slope : 1.f;
@@ -444,7 +476,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           float4 x = lds128(stage + ((RPI * i + sub_r) * ST + c4) * 4);
           x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
           if (p.residual) {
+#ifdef PM_TC_EPI_PREFETCH
+            const float4 t = rres[i];
+#else
             const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
+#endif
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           }
           x.x = fmaxf(x.x, 0.f) + s0 * fminf(x.x, 0.f);
