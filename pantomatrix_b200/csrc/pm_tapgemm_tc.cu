@@ -23,6 +23,10 @@
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
 
+#if defined(PM_TC_TMA_STORE) && !defined(PM_TC_EPI_PREFETCH)
+#define PM_TC_EPI_PREFETCH 1   // the TMA-store epilogue builds on the prefetching loop structure
+#endif
+
 namespace {
 
 constexpr int BM = 128;             // tile rows (UMMA M)
@@ -46,6 +50,9 @@ struct TcParams {
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
   int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
   int pdl;      // launched with programmatic stream serialization: prologue overlaps the previous kernel's tail
+#ifdef PM_TC_TMA_STORE
+  int tma_ok;   // output tensor maps are valid for every requested output and the staging fits the operand ring
+#endif
 };
 
 // Instrumented build only (-DPM_TC_TIMING, tools/gemm_timeline.py): per-CTA clock64 stamps of the kernel's phases.
@@ -181,6 +188,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+#ifdef PM_TC_TMA_STORE
+// Epilogue variant (unmeasured, -DPM_TC_TMA_STORE): results leave through the TMA engine.  Each epilogue warp
+// finishes its 32 x 32 chunk in the TMEM row layout (lane = row), writes it into a swizzled staging tile and one lane
+// issues cp.async.bulk.tensor stores (fp32 tile + one per bf16 plane); out-of-range rows / columns are clipped by
+// the tensor map, so there is no per-element tail code on this path.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+#endif
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
@@ -188,6 +215,10 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tme
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
+#ifdef PM_TC_TMA_STORE
+                                                                    const __grid_constant__ CUtensorMap map_o,
+                                                                    const __grid_constant__ CUtensorMap map_p,
+#endif
                                                                     const TcParams p) {
   constexpr int W_TILE_BYTES = BN * BK * 2;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -378,9 +409,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     constexpr int RPI = 32 / LPR;                                  // rows written per warp-wide store
     constexpr int NIT = 32 / RPI;                                  // store rounds per chunk
     constexpr int ST = CW + 4;                                     // staging row stride (floats): 16B aligned, conflict-free
+#ifndef PM_TC_TMA_STORE
     const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // <= 4.6 KB per warp (shared-space address)
+#endif
     const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;           // this lane's row-in-group / first column of its float4
     const int r_shift = 31 - __clz(p.R);                           // R is a power of two
+#ifdef PM_TC_TMA_STORE
+    constexpr int NCH = BN / 2 / CW;                               // chunks per warp, each with its own staging slot
+    constexpr int CHUNK_STAGE = CW == 32 ? 4096 + 3 * 2048 : 3072; // fp32 tile + 3 plane tiles | legacy transpose tile
+    const uint32_t stage_warp = smem_u32(tiles) + (warp - 2) * NCH * CHUNK_STAGE;
+    const int rt_l = q * 32 + lane;                                // this lane's tile row in the TMEM layout
+    const int b_l = b0 + (rt_l >> r_shift), l_l = l0 + (rt_l & (p.R - 1));
+    const bool row_l_ok = b_l < p.batch && l_l < p.rows_out;
+    const long long off_rl = (long long)b_l * p.r_bs + (long long)l_l * p.ldr;
+    bool did_tma = false;
+#endif
     const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
     const bool vec_r = p.residual && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
     const bool vec_b = p.out_bf16 && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0) &&
@@ -411,19 +454,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       const int nb = n0 + c0;                                                      // first column of this chunk
       const int n = nb + c4;                                                       // this lane's first column
       const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
+#ifdef PM_TC_TMA_STORE
+      const uint32_t stage = stage_warp + ((c0 - half * (BN / 2)) / CW) * CHUNK_STAGE;
+      const bool use_tma = CW == 32 && p.tma_ok && nb + 32 <= p.cout;              // warp-uniform
+      float4 add4[8];                                              // bias of the 32 columns + residual of my row
+      if (use_tma) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          add4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.residual && row_l_ok) {
+            const float4 t = *reinterpret_cast<const float4*>(p.residual + off_rl + nb + 4 * j);
+            add4[j].x += t.x; add4[j].y += t.y; add4[j].z += t.z; add4[j].w += t.w;
+          }
+        }
+      }
+#else
+      constexpr bool use_tma = false;
+#endif
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) {
+      if (!use_tma && p.bias) {
         if (n < p.cout) bias4.x = __ldg(p.bias + n);
         if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
         if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
         if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
       }
+#ifndef PM_TC_TMA_STORE                                            // (register budget: the TMA build keeps its own addends)
       float4 rres[NIT];
-      if (fast && p.residual) {
+      if (!use_tma && fast && p.residual) {
 #pragma unroll
         for (int i = 0; i < NIT; ++i)
           rres[i] = ((row_ok >> i) & 1u) ? *reinterpret_cast<const float4*>(p.residual + off_r[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#endif
       if (c0 == half * (BN / 2)) {
         mbar_wait(smem_u32(acc_bar), 0);
         tc_fence_after();
@@ -448,6 +510,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       const int nb = n0 + c0;                                                      // first column of this chunk
 #endif
       if (nb >= p.cout) continue;                                   // warp-uniform
+#ifdef PM_TC_TMA_STORE
+      if (use_tma) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                               // bias, residual, activation in the row layout
+          const int nj = nb + 4 * j;
+          const float t0 = nj < p.act_cols ? act_slope : 1.f, t1 = nj + 1 < p.act_cols ? act_slope : 1.f;
+          const float t2 = nj + 2 < p.act_cols ? act_slope : 1.f, t3 = nj + 3 < p.act_cols ? act_slope : 1.f;
+          const float x0 = v[4 * j] + add4[j].x, x1 = v[4 * j + 1] + add4[j].y;
+          const float x2 = v[4 * j + 2] + add4[j].z, x3 = v[4 * j + 3] + add4[j].w;
+          v[4 * j] = fmaxf(x0, 0.f) + t0 * fminf(x0, 0.f);
+          v[4 * j + 1] = fmaxf(x1, 0.f) + t1 * fminf(x1, 0.f);
+          v[4 * j + 2] = fmaxf(x2, 0.f) + t2 * fminf(x2, 0.f);
+          v[4 * j + 3] = fmaxf(x3, 0.f) + t3 * fminf(x3, 0.f);
+        }
+        if (p.out_f32) {                                            // [32 rows][128 B], 128-byte swizzle
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(stage + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.out_bf16) {
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            if (pl >= p.out_nsplit) break;
+            const uint32_t st_p = stage + 4096 + pl * 2048;         // [32 rows][64 B], 64-byte swizzle
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
+                w[h] = *reinterpret_cast<const uint32_t*>(&t);
+                v[8 * j + 2 * h] -= __low2float(t);
+                v[8 * j + 2 * h + 1] -= __high2float(t);
+              }
+              sts128u(st_p + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+        fence_async_smem();                                         // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          const int rt0 = q * 32;
+          const int bs = b0 + (rt0 >> r_shift), ls = l0 + (rt0 & (p.R - 1));
+          if (p.out_f32) tma_store_3d(&map_o, stage, nb, ls, bs);
+          if (p.out_bf16)
+            for (int pl = 0; pl < p.out_nsplit; ++pl) tma_store_4d(&map_p, stage + 4096 + pl * 2048, nb, ls, bs, pl);
+          tma_store_commit();
+        }
+        did_tma = true;
+        continue;
+      }
+#endif
       // transpose: thread = row -> smem[row][0..CW)
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -476,7 +590,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           float4 x = lds128(stage + ((RPI * i + sub_r) * ST + c4) * 4);
           x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
           if (p.residual) {
-#ifdef PM_TC_EPI_PREFETCH
+#if defined(PM_TC_EPI_PREFETCH) && !defined(PM_TC_TMA_STORE)
             const float4 t = rres[i];
 #else
             const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
@@ -519,6 +633,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         }
       }
     }
+#ifdef PM_TC_TMA_STORE
+    if (did_tma && lane == 0) tma_store_wait_all();                // staging tiles stay valid until the engine has read them
+#endif
   }
 
   if (warp == 2) PM_STAMP(5);                                     // this warp's share of the epilogue issued
@@ -589,14 +706,40 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+#ifdef PM_TC_TMA_STORE
+bool encode_store_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void* base, int rank,
+                      const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  return fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+struct StoreMaps { CUtensorMap o, p; };
+#define PM_TC_STORE_ARGS , const StoreMaps& sm
+#define PM_TC_STORE_PASS , sm.o, sm.p
+#else
+#define PM_TC_STORE_ARGS
+#define PM_TC_STORE_PASS
+#endif
+
 template <int BN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st PM_TC_STORE_ARGS) {
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
   int stages = (env_kb * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return PM_EUNSUPPORTED;
   p.stages = stages;
+#ifdef PM_TC_TMA_STORE
+  {   // per-chunk staging slots of all 8 epilogue warps (fp32 tile + 3 plane tiles per 32-column chunk) live in
+      // the operand ring, which is idle by then
+    constexpr int CWh = BN == 96 ? 16 : 32;
+    const size_t need = (size_t)8 * (BN / 2 / CWh) * (CWh == 32 ? 4096 + 3 * 2048 : 3072);
+    if (need > (size_t)stages * stage_bytes) return PM_EUNSUPPORTED;
+    if (BN == 96) p.tma_ok = 0;          // 16-column chunks stay on the st.global path
+  }
+#endif
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
@@ -629,10 +772,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     }
     cfg.attrs = attr;
     cfg.numAttrs = n;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN>, ma, mw, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN>, ma, mw PM_TC_STORE_PASS, p);
     return e == cudaSuccess ? PM_OK : (int)e;
   }
-  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
+  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ma, mw PM_TC_STORE_PASS, p);
   PM_LAUNCH_CHECK();
 }
 
@@ -719,9 +862,46 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
+#ifdef PM_TC_TMA_STORE
+  StoreMaps sm;
+  memset(&sm, 0, sizeof(sm));
+  {
+    const int RB = R < 32 ? R : 32, CB = 32 / RB;       // rows / clips of one warp's 32-row store box
+    bool ok = !getenv("PM_TC_NO_TMA_STORE");
+    ok = ok && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+    ok = ok && (!residual || ((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (ldr & 3) == 0 && (batch == 1 || (r_bs & 3) == 0)));
+    if (ok && out_f32) {
+      ok = (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && (ldo & 3) == 0 && (batch == 1 || (o_bs & 3) == 0);
+      if (ok) {
+        const long long bs_el = batch > 1 ? o_bs : (long long)rows_out * ldo;
+        cuuint64_t dims[3] = {(cuuint64_t)cout, (cuuint64_t)rows_out, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)bs_el * 4};
+        cuuint32_t box[3] = {32, (cuuint32_t)RB, (cuuint32_t)CB};
+        ok = encode_store_map(&sm.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, out_f32, 3, dims, strides, box);
+      }
+    }
+    if (ok && out_bf16) {
+      ok = (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0 && (ldob & 7) == 0 && (batch == 1 || (ob_bs & 7) == 0) &&
+           (out_nsplit == 1 || (ob_ps & 7) == 0);
+      if (ok) {
+        const long long bs_el = batch > 1 ? ob_bs : (long long)rows_out * ldob;
+        const long long ps_el = out_nsplit > 1 ? ob_ps : bs_el * batch;
+        cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)rows_out, (cuuint64_t)batch, (cuuint64_t)out_nsplit};
+        cuuint64_t strides[3] = {(cuuint64_t)ldob * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)RB, (cuuint32_t)CB, 1};
+        ok = encode_store_map(&sm.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, out_bf16, 4, dims, strides, box);
+      }
+    }
+    p.tma_ok = ok ? 1 : 0;
+  }
+  if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream, sm);
+  if (BNsel == 96) return launch<96>(ma, mw, p, grid, (cudaStream_t)stream, sm);
+  return launch<128>(ma, mw, p, grid, (cudaStream_t)stream, sm);
+#else
   if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream);
   if (BNsel == 96) return launch<96>(ma, mw, p, grid, (cudaStream_t)stream);
   return launch<128>(ma, mw, p, grid, (cudaStream_t)stream);
+#endif
 }
 
 #ifdef PM_TC_TIMING
