@@ -10,6 +10,7 @@ import torch.nn.functional as F
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
 launch_count = 0
+PLANE_DTYPE = torch.bfloat16      # tests/diag_split_formats.py emulates other operand formats through this and _split
 
 from pantomatrix_b200.ops import Act, PackedW, Planes, _round_up  # noqa: E402,F401  (same containers as the product)
 
@@ -17,7 +18,7 @@ from pantomatrix_b200.ops import Act, PackedW, Planes, _round_up  # noqa: E402,F
 def _split(v, nsplit):
     planes, rem = [], v
     for _ in range(nsplit):
-        p = rem.to(torch.bfloat16)
+        p = rem.to(PLANE_DTYPE)
         planes.append(p)
         rem = rem - p.float()
     return planes
@@ -27,7 +28,7 @@ def _mk_planes(y, nsplit, slack_rows=0):
     """(batch, rows, ch) fp32 -> Planes with NaN-poisoned padding (catches reads of uninitialised memory)."""
     batch, rows, ch = y.shape
     ld = _round_up(ch, 8)
-    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=torch.bfloat16)
+    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=PLANE_DTYPE)
     buf[:, batch * rows:] = 0
     for i, p in enumerate(_split(y.reshape(batch * rows, ch).float(), nsplit)):
         buf[i, :batch * rows, :ch] = p
