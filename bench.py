@@ -34,11 +34,13 @@ N_SAMPLES = 160000                    # 10 s @ 16 kHz -> 300 frames
 FRAMES_PER_CLIP = 300
 FLOP_PER_FRAME = 364.7e6              # algorithmic work per emitted frame
 DTYPES = {"fp32": "f32", "bf16x6": "bf16x6 (split-bf16 operands, f32 accumulate)",
-          "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)", "bf16": "bf16"}
+          "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)", "bf16": "bf16",
+          "fp16x3": "fp16x3 (split-fp16 operands, f32 accumulate; experimental)"}
 ENGINES = {"fp32": "fp32 SIMT tap-GEMM", "bf16x6": "tcgen05 tap-GEMM, 6 bf16 products per fp32 product",
-           "bf16x3": "tcgen05 tap-GEMM, 3 bf16 products per fp32 product", "bf16": "tcgen05 tap-GEMM, plain bf16"}
+           "bf16x3": "tcgen05 tap-GEMM, 3 bf16 products per fp32 product", "bf16": "tcgen05 tap-GEMM, plain bf16",
+           "fp16x3": "tcgen05 tap-GEMM, 3 fp16 products per fp32 product"}
 NCU_TRAFFIC_BYTES = {"bf16x6": 26.4e6}          # per launch, see roofline.traffic_note
-MMA_PER_PRODUCT = {"fp32": 0, "bf16": 1, "bf16x3": 3, "bf16x6": 6}
+MMA_PER_PRODUCT = {"fp32": 0, "bf16": 1, "bf16x3": 3, "bf16x6": 6, "fp16x3": 3}
 METRIC = "motion_frames_per_sec"
 UNIT = "frames/s"
 

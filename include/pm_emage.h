@@ -16,6 +16,10 @@
  *   - optional split-bf16 output (`planes`, p_ps, p_ld, p_nsplit): the producer also (or only, when its fp32
  *     `out` is NULL) writes its result as p_nsplit bf16 planes (x ~ p0+p1+p2, plane stride p_ps, row stride
  *     p_ld elements): the A operand format of pm_tapgemm_tc, so no separate conversion pass is needed
+ *   - plane element format: bit 8 (PM_FMT_F16) of any `nsplit` / `p_nsplit` / `out_nsplit` argument selects IEEE fp16
+ *     planes instead of bf16 (same 2-byte storage).  Two fp16 planes carry 22 mantissa bits, so nsplit = 2
+ *     (3 tensor-core products) gives the accuracy of 3 bf16 planes (6 products) - provided magnitudes stay below
+ *     65504; an overflow becomes inf - inf = NaN in the consuming GEMM, which the host checks for.
  */
 #ifndef PM_EMAGE_H
 #define PM_EMAGE_H
@@ -24,7 +28,8 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
+#define PM_FMT_F16 0x100
 int pm_abi_version(void);
 /* compute capability major*10+minor of the current device, or <0 */
 int pm_device_cc(void);
@@ -55,12 +60,14 @@ int pm_tapgemm_f32(const float* A, long long a_bs, int lda, int batch, int rows_
  * Operands are staged by TMA (cp.async.bulk.tensor, zero fill for padding rows, tap shift folded into the
  * row coordinate); descriptors are built on the host inside this call from the raw pointers.
  * `prefetch` (nullable, 16-byte aligned): prefetch_bytes of global memory - the NEXT GEMM's packed weights - are
- * pulled into L2 by this launch (cp.async.bulk.prefetch.L2), so weight streaming overlaps the previous GEMM. */
+ * pulled into L2 by this launch (cp.async.bulk.prefetch.L2), so weight streaming overlaps the previous GEMM.
+ * fp16 operands (nsplit | PM_FMT_F16): the host packs W scaled by a power of two into the top of the fp16 range;
+ * `acc_scale` (its reciprocal, exact) multiplies the accumulator before bias.  Must be 1 for bf16 operands. */
 int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, int lda, int batch, int rows_in, int cin,
                   const uint16_t* W, long long w_ps, int w_rows, int ldw, int taps, int pad, int nsplit,
                   const float* bias, int rows_out, int cout,
                   const float* residual, long long r_bs, int ldr,
-                  int act, int act_cols, float slope,
+                  int act, int act_cols, float slope, float acc_scale,
                   float* out_f32, long long o_bs, int ldo,
                   uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
                   const void* prefetch, long long prefetch_bytes, void* stream);

@@ -11,6 +11,7 @@ constexpr int HD = 192;
 constexpr int HDP = HD + 1;     // +1 float: conflict-free column walks over rows
 constexpr int NT = 256;
 
+template <bool F16>
 __global__ void __launch_bounds__(NT) attention_f32_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
     const float* __restrict__ V, int ldv, float* __restrict__ O, int ldo,
@@ -121,10 +122,10 @@ __global__ void __launch_bounds__(NT) attention_f32_kernel(
       const long long row = (long long)b * tq + r;
       if (O) *reinterpret_cast<float4*>(O + row * ldo + h * HD + c4 * 4) = v;
       if (P.ptr) {
-        if (vec_p) pm_store_planes4(P, row, h * HD + c4 * 4, v);
+        if (vec_p) pm_store_planes4_t<F16>(P, row, h * HD + c4 * 4, v);
         else {
-          pm_store_planes(P, row, h * HD + c4 * 4, v.x); pm_store_planes(P, row, h * HD + c4 * 4 + 1, v.y);
-          pm_store_planes(P, row, h * HD + c4 * 4 + 2, v.z); pm_store_planes(P, row, h * HD + c4 * 4 + 3, v.w);
+          pm_store_planes_t<F16>(P, row, h * HD + c4 * 4, v.x); pm_store_planes_t<F16>(P, row, h * HD + c4 * 4 + 1, v.y);
+          pm_store_planes_t<F16>(P, row, h * HD + c4 * 4 + 2, v.z); pm_store_planes_t<F16>(P, row, h * HD + c4 * 4 + 3, v.w);
         }
       }
     }
@@ -139,6 +140,7 @@ extern "C" int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk
                                 float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim,
                                 uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE(Q && K && V && (O || planes) && batch >= 0 && heads > 0);
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, heads * head_dim, false));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (head_dim != HD || tq > TMAX || tk > TMAX || tq <= 0 || tk <= 0) return PM_EUNSUPPORTED;
@@ -146,12 +148,16 @@ extern "C" int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk
   if (batch == 0) return PM_OK;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  attention_f32_kernel<<<batch * heads, NT, kSmemBytes, (cudaStream_t)stream>>>(
+  if (f16) attention_f32_kernel<true><<<batch * heads, NT, kSmemBytes, (cudaStream_t)stream>>>(
+      Q, ldq, K, ldk, V, ldv, O, ldo, heads, tq, tk, 1.0f / sqrtf((float)head_dim), P);
+  else attention_f32_kernel<false><<<batch * heads, NT, kSmemBytes, (cudaStream_t)stream>>>(
       Q, ldq, K, ldk, V, ldv, O, ldo, heads, tq, tk, 1.0f / sqrtf((float)head_dim), P);
   PM_LAUNCH_CHECK();
 }

@@ -1,6 +1,7 @@
 // Shared helpers for the EMAGE hot-path kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -58,28 +59,69 @@ __device__ __forceinline__ void pm_split3(float v, __nv_bfloat16 (&p)[3]) {
   p[2] = __float2bfloat16_rn(r);
 }
 
+// Plane element format.  bf16 (default) needs 3 planes / 6 products for an fp32-quality GEMM; IEEE fp16 reaches the
+// same accuracy with 2 planes / 3 products (11-bit mantissas) as long as magnitudes stay below 65504 - an overflow
+// turns into inf - inf = NaN in the consumer GEMM and is caught by the host (profiles/split_formats_r1.json).
+// Callers select it with bit 8 of an `nsplit` argument of the C ABI.
+#ifndef PM_FMT_F16
+#define PM_FMT_F16 0x100
+#endif
+// host side: strip the format bit of an `nsplit` ABI argument into a flag
+#define PM_TAKE_FMT(nsplit_var, flag_var)                          \
+  const bool flag_var = ((nsplit_var) & PM_FMT_F16) != 0;          \
+  (nsplit_var) &= 0xff
+
 // Successive planes are peeled off a running remainder: no dynamically indexed temporaries (they would live in
 // local memory).
-__device__ __forceinline__ void pm_store_planes(const PmPlanes& P, long long row, int c, float v) {
-  __nv_bfloat16* o = P.ptr + row * P.ld + c;
-  for (int pl = 0; pl < P.nsplit; ++pl) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    o[(long long)pl * P.ps] = h;
-    v -= __bfloat162float(h);
+template <bool F16>
+__device__ __forceinline__ void pm_store_planes_t(const PmPlanes& P, long long row, int c, float v) {
+  if constexpr (F16) {
+    __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
+    for (int pl = 0; pl < P.nsplit; ++pl) {
+      const __half h = __float2half_rn(v);
+      o[(long long)pl * P.ps] = h;
+      v -= __half2float(h);
+    }
+  } else {
+    __nv_bfloat16* o = P.ptr + row * P.ld + c;
+    for (int pl = 0; pl < P.nsplit; ++pl) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      o[(long long)pl * P.ps] = h;
+      v -= __bfloat162float(h);
+    }
   }
+}
+__device__ __forceinline__ void pm_store_planes(const PmPlanes& P, long long row, int c, float v) {
+  pm_store_planes_t<false>(P, row, c, v);
 }
 
 // 4 consecutive channels, c % 4 == 0, ld % 4 == 0, ps % 4 == 0, 8-byte aligned base
-__device__ __forceinline__ void pm_store_planes4(const PmPlanes& P, long long row, int c, float4 v) {
-  __nv_bfloat16* o = P.ptr + row * P.ld + c;
-  for (int pl = 0; pl < P.nsplit; ++pl) {
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 w;
-    w.x = *reinterpret_cast<const uint32_t*>(&lo);
-    w.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = w;
-    v.x -= __low2float(lo); v.y -= __high2float(lo); v.z -= __low2float(hi); v.w -= __high2float(hi);
+template <bool F16>
+__device__ __forceinline__ void pm_store_planes4_t(const PmPlanes& P, long long row, int c, float4 v) {
+  if constexpr (F16) {
+    __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
+    for (int pl = 0; pl < P.nsplit; ++pl) {
+      const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&lo);
+      w.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = w;
+      v.x -= __low2float(lo); v.y -= __high2float(lo); v.z -= __low2float(hi); v.w -= __high2float(hi);
+    }
+  } else {
+    __nv_bfloat16* o = P.ptr + row * P.ld + c;
+    for (int pl = 0; pl < P.nsplit; ++pl) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 w;
+      w.x = *reinterpret_cast<const uint32_t*>(&lo);
+      w.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(o + (long long)pl * P.ps) = w;
+      v.x -= __low2float(lo); v.y -= __high2float(lo); v.z -= __low2float(hi); v.w -= __high2float(hi);
+    }
   }
+}
+__device__ __forceinline__ void pm_store_planes4(const PmPlanes& P, long long row, int c, float4 v) {
+  pm_store_planes4_t<false>(P, row, c, v);
 }
 
 static inline bool pm_planes_ok(const void* ptr, long long ps, int ld, int nsplit, int ch, bool vec4) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) wav_stem_kernel(
 // ---------------------------------------------------------------------------------------------------
 // out = LayerNorm(x + r): one warp per row, row kept in registers, two-pass mean / variance.
 // ---------------------------------------------------------------------------------------------------
-template <int VEC>   // float4 chunks per lane: ch = VEC * 128
+template <int VEC, bool F16>   // float4 chunks per lane: ch = VEC * 128; plane format
 __global__ void __launch_bounds__(256) add_layernorm_kernel(
     const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
     const float* __restrict__ beta, float* __restrict__ out, long long rows, float eps, PmPlanes P) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(
     o.z = (v[i].z - mean) * rstd * g.z + bb.z;
     o.w = (v[i].w - mean) * rstd * g.w + bb.w;
     if (o4) o4[lane + 32 * i] = o;
-    if (P.ptr) pm_store_planes4(P, row, (lane + 32 * i) * 4, o);
+    if (P.ptr) pm_store_planes4_t<F16>(P, row, (lane + 32 * i) * 4, o);
   }
 }
 
@@ -104,6 +104,7 @@ __device__ __forceinline__ float4 pick_row(int code, const float* pe, const floa
   return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) add_rows_kernel(
     const float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ spk,
     int first, int second, float* __restrict__ out, int batch, int rows, int ch, PmPlanes P) {
@@ -124,11 +125,12 @@ __global__ void __launch_bounds__(256) add_rows_kernel(
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
     if (out) reinterpret_cast<float4*>(out)[i] = v;
-    if (P.ptr) pm_store_planes4(P, bt, c4 * 4, v);
+    if (P.ptr) pm_store_planes4_t<F16>(P, bt, c4 * 4, v);
   }
 }
 
 // rows x ch (ch % 4 == 0 when planes are requested; otherwise the tensor is treated as one flat row)
+template <bool F16>
 __global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                    float* __restrict__ out, long long n4, long long n, int ch4,
                                                    PmPlanes P) {
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, 
     const float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
     const float4 o = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
     if (out) reinterpret_cast<float4*>(out)[i] = o;
-    if (P.ptr) pm_store_planes4(P, i / ch4, (int)(i % ch4) * 4, o);
+    if (P.ptr) pm_store_planes4_t<F16>(P, i / ch4, (int)(i % ch4) * 4, o);
   }
   // scalar tail (n not a multiple of 4; never with planes)
   if (blockIdx.x == 0 && out) {
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) add2_kernel(const float* __restrict__ a, 
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) window_input_kernel(
     const float* __restrict__ motion, const float* __restrict__ mask, const float* __restrict__ seed,
     const float* __restrict__ mask_embedding, float* __restrict__ out,
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) window_input_kernel(
     }
     const float o = (m == 1.f) ? mask_embedding[c] : v;   // M.py:267-268
     if (out) out[i] = o;
-    if (P.ptr) pm_store_planes(P, bf, c, o);
+    if (P.ptr) pm_store_planes_t<F16>(P, bf, c, o);
   }
 }
 
@@ -197,6 +200,7 @@ extern "C" int pm_add_layernorm_f32(const float* x, const float* r, const float*
                                     float* out, long long rows, int ch, float eps,
                                     uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE(x && gamma && beta && (out || planes) && rows >= 0);
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (rows == 0) return PM_OK;
@@ -204,10 +208,22 @@ extern "C" int pm_add_layernorm_f32(const float* x, const float* r, const float*
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   cudaStream_t st = (cudaStream_t)stream;
   switch (ch) {
-    case 256: add_layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
-    case 512: add_layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
-    case 768: add_layernorm_kernel<6><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
-    case 1024: add_layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P); break;
+    case 256:
+      if (f16) add_layernorm_kernel<2, true><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      else add_layernorm_kernel<2, false><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      break;
+    case 512:
+      if (f16) add_layernorm_kernel<4, true><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      else add_layernorm_kernel<4, false><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      break;
+    case 768:
+      if (f16) add_layernorm_kernel<6, true><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      else add_layernorm_kernel<6, false><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      break;
+    case 1024:
+      if (f16) add_layernorm_kernel<8, true><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      else add_layernorm_kernel<8, false><<<grid, warps * 32, 0, st>>>(x, r, gamma, beta, out, rows, eps, P);
+      break;
     default: return PM_EUNSUPPORTED;
   }
   PM_LAUNCH_CHECK();
@@ -217,6 +233,7 @@ extern "C" int pm_add_rows_f32(const float* x, const float* pe, const float* spk
                                float* out, int batch, int rows, int ch,
                                uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE((out || planes) && batch >= 0 && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   PM_REQUIRE(first >= 0 && first <= 2 && second >= 0 && second <= 2);
@@ -224,8 +241,10 @@ extern "C" int pm_add_rows_f32(const float* x, const float* pe, const float* spk
   PM_REQUIRE((first != 2 && second != 2) || spk);
   const long long total = (long long)batch * rows * (ch >> 2);
   if (total == 0) return PM_OK;
-  add_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, spk, first, second, out,
-                                                                        batch, rows, ch, P);
+  if (f16) add_rows_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, spk, first, second, out,
+                                                                                  batch, rows, ch, P);
+  else add_rows_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, pe, spk, first, second, out,
+                                                                               batch, rows, ch, P);
   PM_LAUNCH_CHECK();
 }
 
@@ -233,10 +252,12 @@ extern "C" int pm_add2_f32(const float* a, const float* b, float* out, long long
                            uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE(a && b && (out || planes) && n >= 0);
   PM_REQUIRE(!planes || (ch > 0 && (ch & 3) == 0 && n % ch == 0));
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (n == 0) return PM_OK;
-  add2_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n, planes ? ch / 4 : 1, P);
+  if (f16) add2_kernel<true><<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n, planes ? ch / 4 : 1, P);
+  else add2_kernel<false><<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n, planes ? ch / 4 : 1, P);
   PM_LAUNCH_CHECK();
 }
 
@@ -245,12 +266,15 @@ extern "C" int pm_window_input_f32(const float* motion, const float* mask, const
                                    int start, int win_len, int pre, int ch,
                                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE(motion && mask && mask_embedding && (out || planes) && (seed || pre == 0));
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, false));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   PM_REQUIRE(batch >= 0 && win_len >= 0 && start >= 0 && start + win_len <= total_len && pre >= 0 && ch > 0);
   const long long total = (long long)batch * win_len * ch;
   if (total == 0) return PM_OK;
-  window_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  if (f16) window_input_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, P);
+  else window_input_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, P);
   PM_LAUNCH_CHECK();
 }

@@ -53,6 +53,7 @@ struct TcParams {
 #ifdef PM_TC_TMA_STORE
   int tma_ok;   // output tensor maps are valid for every requested output and the staging fits the operand ring
 #endif
+  float acc_scale;   // fp16 operands: weights are packed scaled by a power of two, undone here (1 for bf16)
 };
 
 // Instrumented build only (-DPM_TC_TIMING, tools/gemm_timeline.py): per-CTA clock64 stamps of the kernel's phases.
@@ -212,7 +213,7 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tme
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
 #ifdef PM_TC_TMA_STORE
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #endif
                                                                     const TcParams p) {
   constexpr int W_TILE_BYTES = BN * BK * 2;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // instruction descriptor: D = f32; A and B format field 1 = bf16, 0 = fp16; K-major A and B; N >> 3; M >> 4
+  constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   // Three fp32 accumulators in TMEM: two "main" ones that take the p0*p0 products of alternate k-iterations
   // and one "correction" accumulator for every cross product.  The tensor core aligns and TRUNCATES addends to
   // the accumulator's exponent on every MMA, a biased error ~2^-25 |acc| per instruction; keeping the 2^-8-scaled
@@ -506,6 +508,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(acc[j]);
       }
+      if constexpr (F16) {                                                         // undo the weight pre-scale (exact)
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] *= p.acc_scale;
+      }
 #ifndef PM_TC_EPI_PREFETCH
       const int nb = n0 + c0;                                                      // first column of this chunk
 #endif
@@ -539,10 +545,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
               uint32_t w[4];
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
-                w[h] = *reinterpret_cast<const uint32_t*>(&t);
-                v[8 * j + 2 * h] -= __low2float(t);
-                v[8 * j + 2 * h + 1] -= __high2float(t);
+                if constexpr (F16) {
+                  const __half2 t = __floats2half2_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
+                  w[h] = *reinterpret_cast<const uint32_t*>(&t);
+                  v[8 * j + 2 * h] -= __low2float(t);
+                  v[8 * j + 2 * h + 1] -= __high2float(t);
+                } else {
+                  const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
+                  w[h] = *reinterpret_cast<const uint32_t*>(&t);
+                  v[8 * j + 2 * h] -= __low2float(t);
+                  v[8 * j + 2 * h + 1] -= __high2float(t);
+                }
               }
               sts128u(st_p + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
             }
@@ -604,7 +617,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off_f[i] + n) = x;
           if (p.out_bf16) {
             const PmPlanes P{p.out_bf16 + off_b[i], p.ob_ps, p.ldob, p.out_nsplit};
-            pm_store_planes4(P, 0, n, x);
+            pm_store_planes4_t<F16>(P, 0, n, x);
           }
         }
       } else if (n < p.cout) {
@@ -628,7 +641,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             if (p.residual) y += p.residual[orr + n + k];
             y = fmaxf(y, 0.f) + (k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) * fminf(y, 0.f);
             if (p.out_f32) p.out_f32[of + n + k] = y;
-            if (P.ptr) pm_store_planes(P, 0, n + k, y);
+            if (P.ptr) pm_store_planes_t<F16>(P, 0, n + k, y);
           }
         }
       }
@@ -653,7 +666,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------
 // fp32 -> bf16 planes.  One CTA row-block per (clip, row tile): no per-element index arithmetic, 16-byte loads,
 // 8-byte stores.  VEC path needs ch % 4 == 0 and 16-byte aligned rows.
-template <bool VEC>
+template <bool VEC, bool F16>
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long x_bs, int ldx, int rows,
                                                          int ch, __nv_bfloat16* __restrict__ out, long long o_ps,
                                                          long long o_bs, int ldo, int nsplit) {
@@ -667,14 +680,14 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
       const int r = (int)(i / ch4), c4 = (int)(i - (long long)r * ch4);
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * ldx + 4 * c4);
       const PmPlanes P{ob, o_ps, ldo, nsplit};
-      pm_store_planes4(P, r, 4 * c4, v);
+      pm_store_planes4_t<F16>(P, r, 4 * c4, v);
     }
   } else {
     const long long total = (long long)rows * ch;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const int r = (int)(i / ch), c = (int)(i - (long long)r * ch);
       const PmPlanes P{ob, o_ps, ldo, nsplit};
-      pm_store_planes(P, r, c, xb[(long long)r * ldx + c]);
+      pm_store_planes_t<F16>(P, r, c, xb[(long long)r * ldx + c]);
     }
   }
 }
@@ -697,12 +710,13 @@ EncodeTiledFn get_encode() {
 }
 
 bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                const cuuint32_t* box) {
+                const cuuint32_t* box, bool f16 = false) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return false;
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-            ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+            const_cast<void*>(base), dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -723,7 +737,7 @@ struct StoreMaps { CUtensorMap o, p; };
 #define PM_TC_STORE_PASS
 #endif
 
-template <int BN>
+template <int BN, bool F16>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st PM_TC_STORE_ARGS) {
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
@@ -743,7 +757,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -772,10 +786,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     }
     cfg.attrs = attr;
     cfg.numAttrs = n;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN>, ma, mw PM_TC_STORE_PASS, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16>, ma, mw PM_TC_STORE_PASS, p);
     return e == cudaSuccess ? PM_OK : (int)e;
   }
-  tapgemm_tc_kernel<BN><<<grid, NUM_THREADS, smem, st>>>(ma, mw PM_TC_STORE_PASS, p);
+  tapgemm_tc_kernel<BN, F16><<<grid, NUM_THREADS, smem, st>>>(ma, mw PM_TC_STORE_PASS, p);
   PM_LAUNCH_CHECK();
 }
 
@@ -785,11 +799,15 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
                              const uint16_t* W, long long w_ps, int w_rows, int ldw, int taps, int pad, int nsplit,
                              const float* bias, int rows_out, int cout,
                              const float* residual, long long r_bs, int ldr,
-                             int act, int act_cols, float slope,
+                             int act, int act_cols, float slope, float acc_scale,
                              float* out_f32, long long o_bs, int ldo,
                              uint16_t* out_bf16, long long ob_ps, long long ob_bs, int ldob, int out_nsplit,
                              const void* prefetch, long long prefetch_bytes, void* stream) {
   PM_REQUIRE(A && W && (out_f32 || out_bf16));
+  PM_TAKE_FMT(nsplit, f16);                 // operand planes: bf16 (default) or fp16
+  PM_TAKE_FMT(out_nsplit, out_f16);
+  PM_REQUIRE(!out_bf16 || out_f16 == f16);  // emitted planes use the operand format
+  PM_REQUIRE(f16 || acc_scale == 1.0f);
   PM_REQUIRE(!prefetch || (prefetch_bytes >= 0 && (reinterpret_cast<uintptr_t>(prefetch) & 15) == 0));
   PM_REQUIRE(batch > 0 && rows_in > 0 && rows_out > 0 && cin > 0 && cout > 0 && taps > 0);
   PM_REQUIRE(nsplit >= 1 && nsplit <= 3 && (!out_bf16 || (out_nsplit >= 1 && out_nsplit <= 3)));
@@ -831,6 +849,7 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.stages = 0;
   p.prefetch = static_cast<const uint8_t*>(prefetch);
   p.prefetch_bytes = prefetch ? prefetch_bytes : 0;
+  p.acc_scale = acc_scale;
   // Thread-block clusters with TMA multicast (W shared across cm row tiles, A across cn column tiles) are
   // implemented and tested but OFF by default: measured on B200 the mainloop is bound by the tensor pipe and the
   // per-stage barrier round trip, not by L2->smem traffic, and 2x2 clusters were 10-25 % slower
@@ -851,14 +870,14 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows_in, (cuuint64_t)batch, (cuuint64_t)nsplit};
     cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(R / p.cn), (cuuint32_t)NB, 1};
-    if (!encode_map(&ma, A, 4, dims, strides, box)) return PM_EBADARG;
+    if (!encode_map(&ma, A, 4, dims, strides, box, f16)) return PM_EBADARG;
   }
   {
     const long long ps_el = nsplit > 1 ? w_ps : (long long)taps * w_rows * ldw;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps * w_rows, (cuuint64_t)nsplit};
     cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ps_el * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BNsel / p.cm), 1};
-    if (!encode_map(&mw, W, 3, dims, strides, box)) return PM_EBADARG;
+    if (!encode_map(&mw, W, 3, dims, strides, box, f16)) return PM_EBADARG;
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
@@ -889,19 +908,24 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
         cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)rows_out, (cuuint64_t)batch, (cuuint64_t)out_nsplit};
         cuuint64_t strides[3] = {(cuuint64_t)ldob * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
         cuuint32_t box[4] = {32, (cuuint32_t)RB, (cuuint32_t)CB, 1};
-        ok = encode_store_map(&sm.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, out_bf16, 4, dims, strides, box);
+        ok = encode_store_map(&sm.p, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                              CU_TENSOR_MAP_SWIZZLE_64B, out_bf16, 4, dims, strides, box);
       }
     }
     p.tma_ok = ok ? 1 : 0;
   }
-  if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream, sm);
-  if (BNsel == 96) return launch<96>(ma, mw, p, grid, (cudaStream_t)stream, sm);
-  return launch<128>(ma, mw, p, grid, (cudaStream_t)stream, sm);
+#define PM_TC_SM , sm
 #else
-  if (BNsel == 64) return launch<64>(ma, mw, p, grid, (cudaStream_t)stream);
-  if (BNsel == 96) return launch<96>(ma, mw, p, grid, (cudaStream_t)stream);
-  return launch<128>(ma, mw, p, grid, (cudaStream_t)stream);
+#define PM_TC_SM
 #endif
+  if (f16) {
+    if (BNsel == 64) return launch<64, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+    if (BNsel == 96) return launch<96, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+    return launch<128, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+  }
+  if (BNsel == 64) return launch<64, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+  if (BNsel == 96) return launch<96, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+  return launch<128, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
 }
 
 #ifdef PM_TC_TIMING
@@ -922,6 +946,7 @@ extern "C" int pm_tc_timing_read(unsigned long long* host) {
 
 extern "C" int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, int ch,
                              uint16_t* out, long long o_ps, long long o_bs, int ldo, int nsplit, void* stream) {
+  PM_TAKE_FMT(nsplit, f16);
   PM_REQUIRE(x && out && batch >= 0 && rows >= 0 && ch > 0 && ldx >= ch && ldo >= ch && nsplit >= 1 && nsplit <= 3);
   if ((long long)batch * rows == 0) return PM_OK;
   PM_REQUIRE(batch <= 65535);
@@ -933,7 +958,13 @@ extern "C" int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch,
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, batch);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-  if (vec) split_bf16_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
-  else split_bf16_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f16) {
+    if (vec) split_bf16_kernel<true, true><<<grid, 256, 0, st>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+    else split_bf16_kernel<false, true><<<grid, 256, 0, st>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+  } else {
+    if (vec) split_bf16_kernel<true, false><<<grid, 256, 0, st>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+    else split_bf16_kernel<false, false><<<grid, 256, 0, st>>>(x, x_bs, ldx, rows, ch, o, o_ps, o_bs, ldo, nsplit);
+  }
   PM_LAUNCH_CHECK();
 }

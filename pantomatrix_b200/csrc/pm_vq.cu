@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict
   if (lane == 0) index[row] = bk;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ codebook,
                                                           const long long* __restrict__ index, long long rows,
                                                           int ch4, float* __restrict__ out, PmPlanes P) {
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     const int c4 = (int)(i % ch4);
     const float4 v = reinterpret_cast<const float4*>(codebook)[index[r] * ch4 + c4];
     if (out) reinterpret_cast<float4*>(out)[i] = v;
-    if (P.ptr) pm_store_planes4(P, r, c4 * 4, v);
+    if (P.ptr) pm_store_planes4_t<F16>(P, r, c4 * 4, v);
   }
 }
 
@@ -178,12 +179,14 @@ extern "C" int pm_gather_rows_f32(const float* codebook, const long long* index,
                                   float* out, uint16_t* planes, long long p_ps, int p_ld, int p_nsplit,
                                   void* stream) {
   PM_REQUIRE(codebook && index && (out || planes) && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (rows == 0) return PM_OK;
   long long g = (rows * (ch >> 2) + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  gather_rows_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
+  if (f16) gather_rows_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
+  else gather_rows_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
   PM_LAUNCH_CHECK();
 }
 

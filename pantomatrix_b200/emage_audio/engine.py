@@ -48,21 +48,37 @@ def wav_out_len(n: int) -> int:
 
 # Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores
 # with plain bf16 / bf16x3 / bf16x6 split operands (see csrc/pm_tapgemm_tc.cu).
-PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3}
+PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3, "fp16x3": 2}
+# "fp16x3" (experimental, not yet measured on hardware): two IEEE fp16 planes, 3 products - the accuracy of bf16x6
+# at the cost of bf16x3 while activations stay below 65504 (profiles/split_formats_r1.json); pipeline.py checks the
+# outputs for the NaN an overflow would leave.
+PLANE_FORMAT = {"fp16x3": "fp16"}
 # Default: bf16x6 - the tensor-core mode that meets the fp32 parity gates.  "fp32" selects the
 # exact-order SIMT engine, "bf16x3" / "bf16" trade accuracy for speed.  PM_EMAGE_PRECISION overrides the default.
 DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "bf16x6")
-_STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True}   # fork: overlap independent branches on side streams
+_STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True,   # fork: overlap independent branches on side streams
+          "precision": DEFAULT_PRECISION}
+ops.set_plane_format(PLANE_FORMAT.get(DEFAULT_PRECISION, "bf16"))
 
 
 def set_precision(name: str) -> None:
     if name not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
     _STATE["nsplit"] = PRECISIONS[name]
+    _STATE["precision"] = name
+    ops.set_plane_format(PLANE_FORMAT.get(name, "bf16"))
 
 
 def get_precision() -> str:
-    return next(k for k, v in PRECISIONS.items() if v == _STATE["nsplit"])
+    name = _STATE.get("precision")
+    if name in PRECISIONS and PRECISIONS[name] == _STATE["nsplit"]:
+        return name
+    return next(k for k, v in PRECISIONS.items() if v == _STATE["nsplit"])     # _STATE["nsplit"] was set directly (tests)
+
+
+def _pk(nsplit: int) -> int:
+    """Cache key of packed weights: split count + plane format."""
+    return nsplit | (ops.FMT_F16 if ops.plane_format() == "fp16" else 0)
 
 
 def _record_stream(obj, stream):
@@ -125,13 +141,14 @@ class _Conv:
             prev._next = self
         _STATE["prev_conv"] = self
         nxt = self._next
-        return nxt._packed[ns].t if (nxt is not None and ns in nxt._packed) else None
+        return nxt._packed[_pk(ns)].t if (nxt is not None and _pk(ns) in nxt._packed) else None
 
     def packed(self, nsplit):
         """bf16 planes for the tensor-core engine.  A stride-s conv is packed as the equivalent stride-1 conv
         over the (rows/s, s*cin) view of its input: tap k = s*q + r lands in tap q, channel block r; taps
         beyond the kernel size are zero."""
-        if nsplit not in self._packed:
+        key = _pk(nsplit)
+        if key not in self._packed:
             w, s = self.w, self.stride
             if s > 1:
                 taps, cout, cin = w.shape
@@ -139,8 +156,8 @@ class _Conv:
                 for k in range(taps):
                     wp[k // s, :, (k % s) * cin:(k % s + 1) * cin] = w[k]
                 w = wp
-            self._packed[nsplit] = ops.PackedW(w, nsplit)
-        return self._packed[nsplit]
+            self._packed[key] = ops.PackedW(w, nsplit)
+        return self._packed[key]
 
     def __call__(self, x, act=ops.ACT_NONE, slope=0.0, residual=None, out=None, want="f", out_slack=0):
         """x: fp32 tensor, ops.Planes or ops.Act.  want: "f" (fp32 tensor returned), "p" (bf16 planes only) or
@@ -201,7 +218,7 @@ def _planes(x, ns, need_slack=0):
         assert x.slack >= need_slack
         return x
     if isinstance(x, ops.Act):
-        if x.p is not None and x.p.nsplit == ns and x.p.slack >= need_slack:
+        if x.p is not None and x.p.nsplit == ns and x.p.slack >= need_slack and x.p.t.dtype == ops._PLANE_DTYPE:
             return x.p
         x = x.f
     return ops.split_bf16(x, ns, slack_rows=need_slack)

@@ -6,6 +6,8 @@ raise (PmError) on any failure - there is no fallback.
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _lib
@@ -15,6 +17,24 @@ ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
 
 # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
 launch_count = 0
+
+# Element format of the tensor-core operand planes: bf16 (default) or IEEE fp16.  Two fp16 planes (3 products)
+# match three bf16 planes (6 products) in accuracy while magnitudes stay below 65504 (include/pm_emage.h).
+FMT_F16 = 0x100
+_PLANE_DTYPE = torch.bfloat16
+
+
+def set_plane_format(name: str) -> None:
+    global _PLANE_DTYPE
+    _PLANE_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}[name]
+
+
+def plane_format() -> str:
+    return "fp16" if _PLANE_DTYPE == torch.float16 else "bf16"
+
+
+def _fmt_bit(t) -> int:
+    return FMT_F16 if t.dtype == torch.float16 else 0
 
 
 def _stream() -> int:
@@ -107,23 +127,24 @@ class Act:
         self.f, self.p = f, p
 
 
-def _new_planes(nsplit, lead_shape, ch, device, slack_rows=0):
+def _new_planes(nsplit, lead_shape, ch, device, slack_rows=0, dtype=None):
     """Planes for an activation of shape (*lead_shape, ch); lead_shape = (batch, rows)."""
     batch, rows = lead_shape
+    dtype = dtype or _PLANE_DTYPE
     ld = _round_up(ch, 8)
     if slack_rows:
-        buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=device, dtype=torch.bfloat16)
+        buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=device, dtype=dtype)
         buf[:, batch * rows:].zero_()
         t = buf[:, :batch * rows].view(nsplit, batch, rows, ld)
     else:
-        t = torch.empty(nsplit, batch, rows, ld, device=device, dtype=torch.bfloat16)
+        t = torch.empty(nsplit, batch, rows, ld, device=device, dtype=dtype)
     return Planes(t, rows, ch, slack_rows)
 
 
 def _pargs(pl):
     if pl is None:
         return None, 0, 0, 0
-    return pl.t.data_ptr(), pl.t.stride(0), pl.t.stride(2), pl.t.shape[0]
+    return pl.t.data_ptr(), pl.t.stride(0), pl.t.stride(2), pl.t.shape[0] | _fmt_bit(pl.t)
 
 
 def _result(f, pl, nsplit):
@@ -291,13 +312,15 @@ def split_bf16(x, nsplit, slack_rows=0):
     pl = _new_planes(nsplit, (batch, rows), ch, x.device, slack_rows)
     x_bs, ldx = _bs_ld(x)
     _call("pm_split_bf16", x.data_ptr(), x_bs, ldx, batch, rows, ch, pl.t.data_ptr(), pl.t.stride(0), pl.t.stride(1),
-          pl.t.stride(2), nsplit, _stream())
+          pl.t.stride(2), nsplit | _fmt_bit(pl.t), _stream())
     return pl
 
 
 class PackedW:
-    """Weights of one tap-GEMM for the tensor-core engine: (nsplit, taps, w_rows, ldw) bf16 planes."""
-    __slots__ = ("t", "taps", "cout", "cin", "w_rows", "ldw")
+    """Weights of one tap-GEMM for the tensor-core engine: (nsplit, taps, w_rows, ldw) bf16 (or fp16) planes.
+    fp16 planes hold W * 2^k with the largest |W| in [16384, 32768) - small weights keep their second plane out of
+    the fp16 subnormals - and `acc_scale` = 2^-k is handed to the kernel's epilogue."""
+    __slots__ = ("t", "taps", "cout", "cin", "w_rows", "ldw", "acc_scale")
 
     def __init__(self, w, nsplit):
         """w: fp32 (taps, cout, cin)."""
@@ -307,9 +330,16 @@ class PackedW:
         self.w_rows, self.ldw = _round_up(cout, bn), _round_up(cin, 8)
         full = torch.zeros(taps, self.w_rows, self.ldw, device=w.device, dtype=torch.float32)
         full[:, :cout, :cin] = w
+        self.acc_scale = 1.0
+        if _PLANE_DTYPE == torch.float16:
+            m = float(full.abs().max())
+            if m > 0.0 and math.isfinite(m):
+                k = math.floor(math.log2(32768.0 / m))
+                full = full * (2.0 ** k)
+                self.acc_scale = 2.0 ** -k
         planes, rem = [], full
         for _ in range(nsplit):                       # round-to-nearest-even, same as the device split
-            p = rem.to(torch.bfloat16)
+            p = rem.to(_PLANE_DTYPE)
             planes.append(p)
             rem = rem - p.float()
         self.t = torch.stack(planes).contiguous()
@@ -322,7 +352,8 @@ def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, ac
     (strided convs pass the (rows/s, s*C) view of the same memory).  Returns (fp32 out | None, Planes | None)."""
     t = a.t
     nsplit, batch = t.shape[0], t.shape[1]
-    assert nsplit == w.t.shape[0], "A and W must use the same split"
+    assert nsplit == w.t.shape[0] and t.dtype == w.t.dtype, "A and W must use the same split and plane format"
+    fmt = _fmt_bit(t)
     rows_a, cin, lda = (a.rows, a.ch, t.stride(2)) if a_view is None else a_view
     if rows_in is not None:
         rows_a = rows_in
@@ -336,17 +367,18 @@ def tapgemm_tc(a: Planes, w: PackedW, bias, *, rows_in=None, rows_out, pad=0, ac
     o_bs, ldo = _bs_ld(out_f) if out_f is not None else (0, 0)
     out_p = None
     if out_nsplit:
-        out_p = _new_planes(out_nsplit, (batch, rows_out), cout, dev, out_slack)
+        out_p = _new_planes(out_nsplit, (batch, rows_out), cout, dev, out_slack, dtype=t.dtype)
     r_bs, ldr = _bs_ld(residual) if residual is not None else (0, 0)
     if residual is not None:
         _chk(residual)
         assert residual.shape == (batch, rows_out, cout)
     _call("pm_tapgemm_tc", t.data_ptr(), t.stride(0), t.stride(1), lda, batch, rows_a, cin,
-          w.t.data_ptr(), w.t.stride(0), w.w_rows, w.ldw, w.taps, pad, nsplit,
-          _ptr(bias), rows_out, cout, _ptr(residual), r_bs, ldr, act, act_cols, float(slope),
+          w.t.data_ptr(), w.t.stride(0), w.w_rows, w.ldw, w.taps, pad, nsplit | fmt,
+          _ptr(bias), rows_out, cout, _ptr(residual), r_bs, ldr, act, act_cols, float(slope), float(w.acc_scale),
           _ptr(out_f), o_bs, ldo,
           None if out_p is None else out_p.t.data_ptr(), 0 if out_p is None else out_p.t.stride(0),
-          0 if out_p is None else out_p.t.stride(1), 0 if out_p is None else out_p.t.stride(2), out_nsplit,
+          0 if out_p is None else out_p.t.stride(1), 0 if out_p is None else out_p.t.stride(2),
+          out_nsplit | (fmt if out_nsplit else 0),
           None if prefetch is None else prefetch.data_ptr(),
           0 if prefetch is None else prefetch.numel() * prefetch.element_size(), _stream())
     return out_f, out_p

@@ -6,8 +6,17 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .emage_audio.engine import PARTS, select_inputs
+
+_OVERFLOW = ("fp16x3: a GEMM operand exceeded the fp16 range (|x| > 65504) and the result is NaN - "
+             "rerun with engine.set_precision('bf16x6')")
+
+
+def _finite_flag(lat):
+    """0-d bool device tensor: every latent / logit is finite.  fp16 operand planes turn an out-of-range activation
+    into inf - inf = NaN in the consuming GEMM; NaN reaches these tensors, so one reduction guards the whole step."""
+    return torch.stack([torch.isfinite(lat[k]).all() for k in sorted(lat)]).all()
 
 
 @torch.no_grad()
@@ -18,6 +27,12 @@ def generate(model, motion_vq, audio, speaker_id=None, masked_motion=None, mask=
     if speaker_id is None:
         speaker_id = torch.zeros(bs, 1, dtype=torch.long, device=dev)                  # T.py:19
     lat = model.inference(audio, speaker_id, motion_vq, masked_motion=masked_motion, mask=mask)
+    generate.finite = None
+    if ops.plane_format() == "fp16":
+        generate.finite = _finite_flag(lat)
+        capturing = lat["rec_face"].is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing and not bool(generate.finite):
+            raise _lib.PmError(_OVERFLOW)
     cfg = model.cfg.to_dict()
     idx = {p: ops.row_argmax(lat["cls_" + p]) for p in PARTS}                          # T.py:39-42
     index, latent = select_inputs(cfg, lat, idx)
@@ -28,6 +43,9 @@ def generate(model, motion_vq, audio, speaker_id=None, masked_motion=None, mask=
         hands_latent=latent["hands"], face_index=index["face"], upper_index=index["upper"],
         lower_index=index["lower"], hands_index=index["hands"], get_global_motion=True, ref_trans=ref_trans)
     return lat, pred
+
+
+generate.finite = None
 
 
 class CapturedPipeline:
@@ -58,6 +76,7 @@ class CapturedPipeline:
         with torch.cuda.graph(self.graph):
             self.latent, self.pred = generate(model, motion_vq, self.audio, self.speaker_id, ref_trans=self.ref_trans)
         self.kernels_per_replay = ops.launch_count - before
+        self.finite = generate.finite                        # fp16 planes only: in-graph overflow flag (else None)
 
     @torch.no_grad()
     def __call__(self, audio, speaker_id=None):
@@ -67,4 +86,6 @@ class CapturedPipeline:
             self.speaker_id.copy_(speaker_id, non_blocking=True)
         self.graph.replay()
         ops.launch_count += self.kernels_per_replay
+        if self.finite is not None and not bool(self.finite):       # one 1-byte read back per step (fp16 planes only)
+            raise _lib.PmError(_OVERFLOW)
         return self.latent, self.pred

@@ -4,7 +4,7 @@ stand-ins the host-logic tests use) and swaps the emulated operand split:
 
   bf16x6   3 bf16 planes, 6 products (the shipped default)        bf16x3   2 bf16 planes, 3 products
   fp16x3   2 fp16 planes, 3 products; weights scaled per tensor by a power of two into the top of the fp16 range,
-           activations scaled by (none | a fixed 2^4 | a per-tensor power of two)
+           activations scaled by (none | a fixed 2^4 | a per-tensor power of two); "nothing-scaled" = raw fp16 casts
 
 Every window of a 2-clip case is teacher-forced on the float64 oracle's inputs; reported: max / rms error of the
 latents and logits against float64 and the number of emitted codes that differ.  Products are accumulated in fp32
@@ -51,7 +51,10 @@ def make_splitter(fmt, act_policy):
                 planes.append(p)
                 rem = rem - p
             return planes
-        scale = _pow2_scale(v) if (is_weight or act_policy == "dyn") else (16.0 if act_policy == "static16" else 1.0)
+        if act_policy == "raw":                      # nothing scaled at all, weights included
+            scale = 1.0
+        else:
+            scale = _pow2_scale(v) if (is_weight or act_policy == "dyn") else (16.0 if act_policy == "static16" else 1.0)
         planes, rem = [], v * scale
         for _ in range(nsplit):
             p = rem.to(torch.float16).float()           # saturates to inf on overflow, like the hardware convert
@@ -80,6 +83,7 @@ def install(split):
             full = torch.zeros(taps, self.w_rows, self.ldw)
             full[:, :cout, :cin] = w
             self.t = torch.stack(split(full, nsplit, True)).contiguous()
+            self.acc_scale = 1.0                     # the emulated planes are stored de-scaled
     real.PackedW = EmuPackedW
     fake_ops.PackedW = EmuPackedW
     return engine
@@ -94,7 +98,7 @@ def main():
     with torch.no_grad():
         O.emage_generate(sd64, cfg, vq64, audio.double(), spk, trace=tr64)
     modes = [("fp32", 0, "bf16", None), ("bf16x3", 2, "bf16", None), ("bf16x6", 3, "bf16", None),
-             ("fp16x3/act-unscaled", 2, "fp16", "none"), ("fp16x3/act-x16", 2, "fp16", "static16"),
+             ("fp16x3/nothing-scaled", 2, "fp16", "raw"), ("fp16x3/act-unscaled", 2, "fp16", "none"), ("fp16x3/act-x16", 2, "fp16", "static16"),
              ("fp16x3/act-per-tensor", 2, "fp16", "dyn")]
     for name, nsplit, fmt, pol in modes:
         engine = install(make_splitter(fmt, pol))

@@ -10,15 +10,20 @@ import torch.nn.functional as F
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 ROW_NONE, ROW_PE, ROW_SPK = 0, 1, 2
 launch_count = 0
-PLANE_DTYPE = torch.bfloat16      # tests/diag_split_formats.py emulates other operand formats through this and _split
+PLANE_DTYPE = None                # None: follow ops.set_plane_format(); tests/diag_split_formats.py overrides it
 
+import pantomatrix_b200.ops as _real  # noqa: E402
 from pantomatrix_b200.ops import Act, PackedW, Planes, _round_up  # noqa: E402,F401  (same containers as the product)
+
+
+def _plane_dtype():
+    return PLANE_DTYPE or _real._PLANE_DTYPE
 
 
 def _split(v, nsplit):
     planes, rem = [], v
     for _ in range(nsplit):
-        p = rem.to(PLANE_DTYPE)
+        p = rem.to(_plane_dtype())
         planes.append(p)
         rem = rem - p.float()
     return planes
@@ -28,7 +33,7 @@ def _mk_planes(y, nsplit, slack_rows=0):
     """(batch, rows, ch) fp32 -> Planes with NaN-poisoned padding (catches reads of uninitialised memory)."""
     batch, rows, ch = y.shape
     ld = _round_up(ch, 8)
-    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=PLANE_DTYPE)
+    buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=_plane_dtype())
     buf[:, batch * rows:] = 0
     for i, p in enumerate(_split(y.reshape(batch * rows, ch).float(), nsplit)):
         buf[i, :batch * rows, :ch] = p
@@ -171,7 +176,7 @@ def tapgemm_tc(a, w, bias, *, rows_in=None, rows_out, pad=0, act=ACT_NONE, act_c
         for j in range(nsplit - i):
             wj = w.t[j, :, :w.cout, :w.cin].float()
             y = y + F.conv1d(xi.transpose(1, 2), wj.permute(1, 2, 0), None, padding=pad).transpose(1, 2)
-    y = y[:, :rows_out]
+    y = y[:, :rows_out] * getattr(w, "acc_scale", 1.0)          # fp16 weights are packed pre-scaled by a power of two
     if bias is not None:
         y = y + bias
     if residual is not None:

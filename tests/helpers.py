@@ -32,3 +32,13 @@ def build_lstm_product(kind, seed=0, device="cuda"):
     from pantomatrix_b200.lstm_audio import CamnAudioConfig, CamnAudioModel, DiscoAudioConfig, DiscoAudioModel
     cls, ccls = (CamnAudioModel, CamnAudioConfig) if kind == "camn" else (DiscoAudioModel, DiscoAudioConfig)
     return load_synthetic(cls(ccls(**LSTM_CFG)), seed, kind).to(device).eval()
+
+
+# Opt-in GPU tests of code paths that have not been measured on hardware yet (fp16 operand planes, 96-column tiles):
+# PM_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu
+import os as _os  # noqa: E402
+
+import pytest as _pytest  # noqa: E402
+
+EXPERIMENTAL = _pytest.mark.skipif(_os.environ.get("PM_TEST_EXPERIMENTAL") != "1",
+                                   reason="experimental path: set PM_TEST_EXPERIMENTAL=1")

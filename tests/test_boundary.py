@@ -84,7 +84,54 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pm_emage.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().pm_abi_version() == 1
+    assert _lib.load().pm_abi_version() == 2
+
+
+def test_ctypes_signatures_match_the_header():
+    """Argument-by-argument: the ctypes binding of every entry point has the C types of its declaration in
+    include/pm_emage.h, and the definitions in csrc/ repeat the declaration (a drifted float / int here would
+    corrupt every later argument of a call)."""
+    import glob
+    from pantomatrix_b200 import _lib
+
+    def protos(text):
+        out = {}
+        for name, args in re.findall(r"\bint\s+(pm_\w+)\s*\(([^)]*)\)", re.sub(r"/\*.*?\*/", "", text, flags=re.S)):
+            kinds = []
+            for a in (x.strip() for x in args.split(",")):
+                if a in ("void", ""):
+                    continue
+                kinds.append("p" if "*" in a else "ll" if "long long" in a else "f" if a.startswith("float") else "i")
+            out[name] = kinds
+        return out
+
+    tag = {ctypes.c_void_p: "p", ctypes.c_longlong: "ll", ctypes.c_float: "f", ctypes.c_int: "i"}
+    header = protos(open(os.path.join(ROOT, "include", "pm_emage.h")).read())
+    for name, args in _lib.SIGNATURES.items():
+        assert [tag[a] for a in args] == header[name], name
+    defined = {}
+    for f in glob.glob(os.path.join(ROOT, "pantomatrix_b200", "csrc", "*.cu")):
+        src = open(f).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        defined.update(protos(src.replace('extern "C" int', "int")))
+    for name, kinds in header.items():
+        assert defined.get(name) == kinds, (name, defined.get(name), kinds)
+
+
+def test_ops_call_sites_pass_the_declared_number_of_arguments():
+    """Every `_call("pm_...", ...)` in pantomatrix_b200/ops.py passes as many arguments as the binding declares
+    (`*_pargs(...)` expands to the 4 plane arguments) - checked statically, since no kernel can be launched here."""
+    import ast
+    from pantomatrix_b200 import _lib
+    tree = ast.parse(open(os.path.join(ROOT, "pantomatrix_b200", "ops.py")).read())
+    seen = set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "_call":
+            name = node.args[0].value
+            n = sum(4 if isinstance(a, ast.Starred) else 1 for a in node.args[1:])
+            assert n == len(_lib.SIGNATURES[name]), (name, n, len(_lib.SIGNATURES[name]))
+            seen.add(name)
+    assert seen == set(_lib.SIGNATURES) - {"pm_abi_version", "pm_device_cc"}, seen ^ set(_lib.SIGNATURES)
 
 
 def test_no_cpu_fallback():

@@ -26,6 +26,8 @@ def cpu_product(monkeypatch):
     monkeypatch.setattr(modeling, "_require_cuda", lambda module, what: torch.device("cpu"))
     from pantomatrix_b200.emage_audio import engine
     monkeypatch.setitem(engine._STATE, "nsplit", 0)      # exact fp32 engine unless a test selects a tensor-core mode
+    monkeypatch.setitem(engine._STATE, "precision", "fp32")
+    monkeypatch.setattr(real, "_PLANE_DTYPE", real._PLANE_DTYPE)   # set_precision() may switch the plane format: restore
     return build_product(seed=0, device="cpu")
 
 
@@ -80,7 +82,7 @@ def test_wav_out_len_matches_reference_geometry():
         assert window_plan(L, 64, 4) == O.window_plan(L, 64, 4)
 
 
-@pytest.mark.parametrize("precision,atol", [("bf16x6", 5e-4), ("bf16x3", 5e-3)])
+@pytest.mark.parametrize("precision,atol", [("bf16x6", 5e-4), ("bf16x3", 5e-3), ("fp16x3", 5e-4)])
 def test_tensor_core_schedule_host_logic(cpu_product, golden_dir, precision, atol):
     """The tensor-core engine's host side (weight packing into padded bf16 planes, strided convs as reshaped
     stride-1 problems, clips-per-tile views) reproduces the reference with the kernels emulated."""
@@ -94,7 +96,7 @@ def test_tensor_core_schedule_host_logic(cpu_product, golden_dir, precision, ato
     for p in PARTS:
         np.testing.assert_allclose(lat["rec_" + p].numpy()[:, ::7], g["rec_" + p], atol=atol, rtol=0)
         agree = (lat["cls_" + p].argmax(-1).numpy() == g["idx_cls_" + p]).mean()
-        assert agree > (0.999 if precision == "bf16x6" else 0.97), (p, agree)
+        assert agree > (0.97 if precision == "bf16x3" else 0.999), (p, agree)
 
 
 @pytest.mark.parametrize("kind", ["camn", "disco"])

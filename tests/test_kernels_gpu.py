@@ -7,6 +7,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from helpers import EXPERIMENTAL  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 
@@ -247,11 +249,20 @@ def _planes_value(pl):
     return pl.t[:, :, :, :pl.ch].float().sum(0)
 
 
+@pytest.fixture()
+def plane_format(request, ops):
+    ops.set_plane_format(request.param)
+    yield request.param
+    ops.set_plane_format("bf16")
+
+
+@pytest.mark.parametrize("plane_format", ["bf16", pytest.param("fp16", marks=EXPERIMENTAL)], indirect=True)
 @pytest.mark.parametrize("nsplit", [1, 2, 3])
-def test_fused_plane_outputs(ops, nsplit):
-    """Producers that write their result directly as split-bf16 planes (the A-operand format of the tensor-core
-    GEMM): planes must re-assemble the fp32 result to 2^-8 / 2^-16 / 2^-24 relative accuracy."""
-    tol = 2.0 ** (-8 * nsplit) * 1.01
+def test_fused_plane_outputs(ops, nsplit, plane_format):
+    """Producers that write their result directly as split planes (the A-operand format of the tensor-core
+    GEMM): planes must re-assemble the fp32 result to 2^-8 / 2^-16 / 2^-24 (bf16) or 2^-11 / 2^-22 / 2^-24 (fp16)
+    relative accuracy."""
+    tol = max(2.0 ** (-(8 if plane_format == "bf16" else 11) * nsplit), 2.0 ** -24) * 1.01
     E = 768
     x, r, g, b = _rand(4, 60, E, seed=50), _rand(4, 60, E, seed=51), _rand(E, seed=52), _rand(E, seed=53)
     ref = ops.add_layernorm(x, r, g, b)
