@@ -289,3 +289,15 @@ def test_fused_plane_outputs(ops, nsplit, plane_format):
     ref = ops.window_input(motion, mask, seed, emb, 60, 64, 4)
     got = ops.window_input(motion, mask, seed, emb, 60, 64, 4, nsplit=nsplit, f32=False)
     assert got.p.t.shape[-1] == 344 and (_planes_value(got.p) - ref).abs().max() <= tol * ref.abs().max()
+
+
+@EXPERIMENTAL
+def test_attention_mma_variant_in_subprocess():
+    """The attention tests again with PM_ATTN_MMA=1 (mma.sync 3xTF32 kernel); the knob is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PM_ATTN_MMA="1", PM_TEST_EXPERIMENTAL="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu",
+                        "-k", "attention or fused_plane"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
