@@ -134,6 +134,53 @@ def test_ops_call_sites_pass_the_declared_number_of_arguments():
     assert seen == set(_lib.SIGNATURES) - {"pm_abi_version", "pm_device_cc"}, seen ^ set(_lib.SIGNATURES)
 
 
+def test_ops_wrappers_marshal_valid_arguments(monkeypatch):
+    """The real pantomatrix_b200.ops wrappers (not the fake ones) executed on CPU tensors with the library call
+    replaced by a recorder: every argument must convert to the ctypes type its binding declares, for bf16 and fp16
+    planes.  Catches marshalling mistakes (a tensor where a pointer is due, None for an int, a missing argument)
+    without a GPU; the kernels themselves are covered by the -m gpu tests."""
+    from pantomatrix_b200 import _lib, ops
+    calls = []
+
+    def record(name, *args):
+        sig = _lib.SIGNATURES[name]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t is ctypes.c_void_p:
+                assert a is None or isinstance(a, int), (name, i, type(a))
+            elif t is ctypes.c_float:
+                assert isinstance(a, float), (name, i, type(a))
+            else:
+                assert isinstance(a, int) and not isinstance(a, bool), (name, i, type(a))
+                t(a)
+        calls.append((name, args))
+
+    monkeypatch.setattr(_lib, "call", record)
+    monkeypatch.setattr(ops, "_chk", lambda t, dtype=torch.float32: t)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "_PLANE_DTYPE", ops._PLANE_DTYPE)
+    for fmt, bit in (("bf16", 0), ("fp16", ops.FMT_F16)):
+        ops.set_plane_format(fmt)
+        calls.clear()
+        x = torch.zeros(2, 64, 768)
+        pl = ops.split_bf16(x, 2)
+        w = ops.PackedW(torch.randn(1, 768, 768) * 0.03, 2)
+        assert (w.acc_scale == 1.0) == (fmt == "bf16")
+        out, planes = ops.tapgemm_tc(pl, w, torch.zeros(768), rows_out=64, act=ops.ACT_RELU, residual=torch.zeros(2, 64, 768),
+                                     out_nsplit=2)
+        assert out.shape == (2, 64, 768) and planes.t.dtype == pl.t.dtype
+        ln = ops.add_layernorm(x, x, torch.ones(768), torch.zeros(768), nsplit=2)
+        att = ops.attention(x.view(128, 768), x.view(128, 768), x.view(128, 768), 2, 4, 64, 64, 192, nsplit=2, f32=False)
+        ops.add2(x, x, nsplit=2)
+        ops.gather_rows(torch.zeros(256, 256), torch.zeros(2, 8, dtype=torch.long), nsplit=2)
+        assert ln.p.t.dtype == att.p.t.dtype == pl.t.dtype
+        by_name = dict(calls)
+        assert by_name["pm_split_bf16"][10] == 2 | bit
+        gemm = by_name["pm_tapgemm_tc"]
+        assert gemm[13] == 2 | bit and gemm[31] == 2 | bit and gemm[23] == float(w.acc_scale)
+        assert by_name["pm_add_layernorm_f32"][11] == 2 | bit and by_name["pm_attention_f32"][16] == 2 | bit
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly off-GPU instead of computing on the CPU."""
     from pantomatrix_b200 import _lib
