@@ -35,6 +35,9 @@ def _pow2_scale(v):
     return 1.0 if m == 0.0 or not math.isfinite(m) else 2.0 ** math.floor(math.log2(FP16_TOP / m))
 
 
+FLUSH = {"on": False}      # emulate a tensor core that flushes fp16 subnormal operands to zero (worst case)
+
+
 def make_splitter(fmt, act_policy):
     """-> split(v, nsplit, is_weight): list of fp32 tensors whose sum approximates v the way the format would."""
     def split(v, nsplit, is_weight):
@@ -58,6 +61,8 @@ def make_splitter(fmt, act_policy):
         planes, rem = [], v * scale
         for _ in range(nsplit):
             p = rem.to(torch.float16).float()           # saturates to inf on overflow, like the hardware convert
+            if FLUSH["on"]:
+                p = torch.where(p.abs() < 2.0 ** -14, torch.zeros_like(p), p)
             planes.append(p / scale)
             rem = rem - p
         return planes
@@ -72,6 +77,7 @@ def install(split):
             setattr(real, name, getattr(fake_ops, name))
     modeling._require_cuda = lambda module, what: torch.device("cpu")
     fake_ops.PLANE_DTYPE = torch.float32
+    real._PLANE_DTYPE = torch.float32             # the emulated planes are stored de-scaled in fp32
     fake_ops._split = lambda v, nsplit: split(v, nsplit, False)
 
     class EmuPackedW(real.PackedW):
@@ -99,8 +105,11 @@ def main():
         O.emage_generate(sd64, cfg, vq64, audio.double(), spk, trace=tr64)
     modes = [("fp32", 0, "bf16", None), ("bf16x3", 2, "bf16", None), ("bf16x6", 3, "bf16", None),
              ("fp16x3/nothing-scaled", 2, "fp16", "raw"), ("fp16x3/act-unscaled", 2, "fp16", "none"), ("fp16x3/act-x16", 2, "fp16", "static16"),
-             ("fp16x3/act-per-tensor", 2, "fp16", "dyn")]
+             ("fp16x3/act-per-tensor", 2, "fp16", "dyn"),
+             ("fp16x3/act-unscaled, subnormals flushed", 2, "fp16", "none"), ("fp16x3/act-x16, subnormals flushed", 2, "fp16", "static16"),
+             ("fp16x3/act-per-tensor, subnormals flushed", 2, "fp16", "dyn")]
     for name, nsplit, fmt, pol in modes:
+        FLUSH["on"] = "flushed" in name
         engine = install(make_splitter(fmt, pol))
         engine._STATE["nsplit"] = nsplit
         model, vqm = build_product(seed=0, device="cpu")

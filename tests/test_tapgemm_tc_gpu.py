@@ -135,3 +135,21 @@ def test_bn96_tiles_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+@EXPERIMENTAL
+def test_fp16_planes_keep_subnormal_second_plane(ops):
+    """fp16x3 leaves activations unscaled, so small activations put their SECOND plane into the fp16 subnormal range.
+    The CPU study (profiles/split_formats_r1.json) shows the mode collapses to bf16x3 quality or worse if those were
+    flushed to zero; this pins that the tensor core honours fp16 subnormal operands (else: scale the activations)."""
+    ops.set_plane_format("fp16")
+    try:
+        x = _rand(1, 256, 768, seed=11, scale=1e-3)               # second plane ~ 2^-12 * 1e-3 = 2.4e-7: subnormal
+        w = _rand(1, 256, 768, seed=12, scale=1 / math.sqrt(768))
+        want = F.linear(x.double(), w[0].double())
+        got, _ = ops.tapgemm_tc(ops.split_bf16(x, 2), ops.PackedW(w, 2), None, rows_out=256)
+        err = (got.double() - want).abs().max().item()
+        assert err <= TOL[3] * float(want.abs().max()), err
+    finally:
+        ops.set_plane_format("bf16")
+
