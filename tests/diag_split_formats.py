@@ -57,7 +57,7 @@ def make_splitter(fmt, act_policy):
         if act_policy == "raw":                      # nothing scaled at all, weights included
             scale = 1.0
         else:
-            scale = _pow2_scale(v) if (is_weight or act_policy == "dyn") else (16.0 if act_policy == "static16" else 1.0)
+            scale = _pow2_scale(v) if (is_weight or act_policy == "dyn") else (float(2 ** int(act_policy[6:])) if act_policy.startswith("static") else 1.0)
         planes, rem = [], v * scale
         for _ in range(nsplit):
             p = rem.to(torch.float16).float()           # saturates to inf on overflow, like the hardware convert
@@ -104,10 +104,12 @@ def main():
     with torch.no_grad():
         O.emage_generate(sd64, cfg, vq64, audio.double(), spk, trace=tr64)
     modes = [("fp32", 0, "bf16", None), ("bf16x3", 2, "bf16", None), ("bf16x6", 3, "bf16", None),
-             ("fp16x3/nothing-scaled", 2, "fp16", "raw"), ("fp16x3/act-unscaled", 2, "fp16", "none"), ("fp16x3/act-x16", 2, "fp16", "static16"),
+             ("fp16x3/nothing-scaled", 2, "fp16", "raw"), ("fp16x3/act-unscaled", 2, "fp16", "none"), ("fp16x3/act-x16", 2, "fp16", "static4"),
              ("fp16x3/act-per-tensor", 2, "fp16", "dyn"),
-             ("fp16x3/act-unscaled, subnormals flushed", 2, "fp16", "none"), ("fp16x3/act-x16, subnormals flushed", 2, "fp16", "static16"),
-             ("fp16x3/act-per-tensor, subnormals flushed", 2, "fp16", "dyn")]
+             ("fp16x3/act-unscaled, subnormals flushed", 2, "fp16", "none"), ("fp16x3/act-x16, subnormals flushed", 2, "fp16", "static4"),
+             ("fp16x3/act-per-tensor, subnormals flushed", 2, "fp16", "dyn"),
+             ("fp16x3/act-x64, subnormals flushed", 2, "fp16", "static6"), ("fp16x3/act-x256, subnormals flushed", 2, "fp16", "static8"),
+             ("fp16x3/act-x256", 2, "fp16", "static8")]
     for name, nsplit, fmt, pol in modes:
         FLUSH["on"] = "flushed" in name
         engine = install(make_splitter(fmt, pol))
