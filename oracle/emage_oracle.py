@@ -351,6 +351,44 @@ def vq_part_decode(vq, part, index=None, latent=None):
     return vq_decoder(sd, "decoder", cb[index], cfg["vae_layer"]), index
 
 
+def split_inputs(rot6d, expression, tar_contact=None, tar_trans=None):
+    """EmageVQModel.spilt_inputs (sic), M.py:97-108: per-part encoder inputs from 55 x rot6d + expression."""
+    bs, t, j6 = rot6d.shape
+    r = rot6d.reshape(bs, t, j6 // 6, 6)
+    contact = torch.zeros(bs, t, 4, dtype=rot6d.dtype) if tar_contact is None else tar_contact
+    trans = torch.zeros(bs, t, 3, dtype=rot6d.dtype) if tar_trans is None else tar_trans
+    return dict(face=torch.cat([r[:, :, 22], expression], dim=2), upper=r[:, :, list(UPPER_JOINTS)].reshape(bs, t, 78),
+                hands=r[:, :, 25:55].reshape(bs, t, 180),
+                lower=torch.cat([r[:, :, list(LOWER_JOINTS)].reshape(bs, t, 54), trans, contact], dim=2))
+
+
+def vqvae_forward(vq, part, inputs):
+    """EmageVQVAEConv.forward, M.py:42-46, with Quantizer.forward P.py:144-156: encoder, nearest code, the
+    straight-through value z + (z_q - z) the decoder actually sees, commitment loss and code perplexity."""
+    sd, cfg = vq[part]
+    cb = sd["quantizer.embedding.weight"]
+    z = vq_encoder(sd, "encoder", inputs, cfg["vae_layer"])
+    index = l2_argmin(z, cb)
+    z_q = cb[index]
+    loss = torch.mean((z_q - z) ** 2) + cfg["vae_quantizer_lambda"] * torch.mean((z_q - z) ** 2)
+    z_st = z + (z_q - z)
+    e_mean = F.one_hot(index.reshape(-1), cb.shape[0]).to(z.dtype).mean(0)
+    perplexity = torch.exp(-torch.sum(e_mean * torch.log(e_mean + 1e-10)))
+    return {"poses_feat": z_st, "embedding_loss": loss, "perplexity": perplexity,
+            "rec_pose": vq_decoder(sd, "decoder", z_st, cfg["vae_layer"]), "_index": index}
+
+
+def vq_tokenise(vq, rot6d, expression, tar_contact=None, tar_trans=None):
+    """EmageVQModel.map2index / map2latent, M.py:110-124: (indices, latents) per part."""
+    parts = split_inputs(rot6d, expression, tar_contact, tar_trans)
+    idx, lat = {}, {}
+    for p in PARTS:
+        sd, cfg = vq[p]
+        idx[p] = l2_argmin(vq_encoder(sd, "encoder", parts[p], cfg["vae_layer"]), sd["quantizer.embedding.weight"])
+        lat[p] = sd["quantizer.embedding.weight"][idx[p]]
+    return idx, lat
+
+
 def vq_decode(vq, face_index=None, upper_index=None, hands_index=None, lower_index=None,
               face_latent=None, upper_latent=None, hands_latent=None, lower_latent=None,
               get_global_motion=False, ref_trans=None):

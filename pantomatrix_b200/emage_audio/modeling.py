@@ -245,12 +245,14 @@ class EmageVQVAEConv(_EngineOwner):
         pre = eng["enc"](inputs.contiguous().float())
         index = self._index_of(pre)
         z_q = ops.gather_rows(eng["cb"], index)
-        # loss / perplexity are reporting scalars off the inference path (P.py:151-155): plain torch
+        # loss / perplexity / the straight-through value are training-side bookkeeping off the inference path
+        # (P.py:151-155): plain torch.  The decoder sees z + (z_q - z), as in the reference, not the bare code.
         beta = float(self.config.vae_quantizer_lambda)
-        loss = torch.mean((z_q - pre) ** 2) * (1.0 + beta)
+        loss = torch.mean((z_q - pre) ** 2) + beta * torch.mean((z_q - pre) ** 2)
+        z_st = (pre + (z_q - pre)).contiguous()
         e_mean = torch.bincount(index.reshape(-1), minlength=eng["cb"].shape[0]).float() / index.numel()
         perplexity = torch.exp(-torch.sum(e_mean * torch.log(e_mean + 1e-10)))
-        return {"poses_feat": z_q, "embedding_loss": loss, "perplexity": perplexity, "rec_pose": eng["dec"](z_q)}
+        return {"poses_feat": z_st, "embedding_loss": loss, "perplexity": perplexity, "rec_pose": eng["dec"](z_st)}
 
 
 class EmageVAEConv(_EngineOwner):

@@ -258,3 +258,24 @@ def test_tensor_core_precision_modes(product, ckpt, precision, rec_tol, min_agre
     print(f"\\n[{precision}] index agreement {same}/{total}, max |rec| error {worst:.3e}")
     assert worst < rec_tol, (precision, worst)
     assert same / total >= min_agree, (precision, same, total)
+
+
+@EXPERIMENTAL
+def test_tokenisation_matches_reference_golden(product, golden_dir):
+    """map2index / map2latent / EmageVQVAEConv.forward on the GPU against the real reference's outputs
+    (tests/golden/case_tokenise.npz); the CPU twin is tests/test_host_logic.py."""
+    _, vqm = product
+    g = np.load(os.path.join(golden_dir, "case_tokenise.npz"))
+    rot6d, expr = torch.from_numpy(g["rot6d"]).cuda(), torch.from_numpy(g["expression"]).cuda()
+    contact, trans = torch.from_numpy(g["tar_contact"]).cuda(), torch.from_numpy(g["tar_trans"]).cuda()
+    idx = vqm.map2index(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    lat = vqm.map2latent(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    parts = vqm.spilt_inputs(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    models = dict(face=vqm.vq_model_face, upper=vqm.vq_model_upper, hands=vqm.vq_model_hands, lower=vqm.vq_model_lower)
+    for p in PARTS:
+        assert np.array_equal(idx[p].cpu().numpy(), g["idx_" + p]), p
+        assert np.array_equal(lat[p].cpu().numpy(), g["latent_" + p]), p
+        fw = models[p].forward(parts[p])
+        np.testing.assert_allclose(fw["rec_pose"].cpu().numpy(), g["rec_pose_" + p], atol=1e-4, rtol=0)
+        np.testing.assert_allclose(float(fw["embedding_loss"]), float(g["embedding_loss_" + p]), rtol=1e-4)
+        np.testing.assert_allclose(float(fw["perplexity"]), float(g["perplexity_" + p]), rtol=1e-4)

@@ -117,3 +117,28 @@ def test_lstm_models_host_logic(kind, cpu_product, golden_dir):
     np.testing.assert_allclose(b["motion"].reshape(bs, t, -1).numpy(), g["seeded_motion"], atol=1e-4, rtol=0)
     np.testing.assert_allclose(a["motion_axis_angle"].numpy(), g["motion_axis_angle"], atol=1e-3, rtol=0)
     assert model(audio, spk, return_axis_angle=False)["motion_axis_angle"] is None
+
+
+def test_tokenisation_host_logic_vs_reference(cpu_product, golden_dir):
+    """EmageVQModel.map2index / map2latent / spilt_inputs and EmageVQVAEConv.forward of the product (kernels emulated)
+    against the real reference's outputs (tests/golden/case_tokenise.npz)."""
+    _, vqm = cpu_product
+    g = np.load(os.path.join(golden_dir, "case_tokenise.npz"))
+    rot6d, expr = torch.from_numpy(g["rot6d"]), torch.from_numpy(g["expression"])
+    contact, trans = torch.from_numpy(g["tar_contact"]), torch.from_numpy(g["tar_trans"])
+    idx = vqm.map2index(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    idx0 = vqm.map2index(rot6d, expr)
+    lat = vqm.map2latent(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    parts = vqm.spilt_inputs(rot6d, expr, tar_contact=contact, tar_trans=trans)
+    models = dict(face=vqm.vq_model_face, upper=vqm.vq_model_upper, hands=vqm.vq_model_hands, lower=vqm.vq_model_lower)
+    for p in PARTS:
+        assert np.array_equal(parts[p].numpy(), g["input_" + p]), p
+        assert np.array_equal(idx[p].numpy(), g["idx_" + p]) and np.array_equal(idx0[p].numpy(), g["idx_default_" + p]), p
+        assert np.array_equal(lat[p].numpy(), g["latent_" + p]), p
+        fw = models[p].forward(parts[p])
+        assert set(fw) == {"poses_feat", "embedding_loss", "perplexity", "rec_pose"}
+        np.testing.assert_allclose(fw["rec_pose"].numpy(), g["rec_pose_" + p], atol=5e-5, rtol=0)
+        np.testing.assert_allclose(fw["poses_feat"].numpy(), g["poses_feat_" + p], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(float(fw["embedding_loss"]), float(g["embedding_loss_" + p]), rtol=1e-5)
+        np.testing.assert_allclose(float(fw["perplexity"]), float(g["perplexity_" + p]), rtol=1e-5)
+

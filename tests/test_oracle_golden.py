@@ -85,3 +85,28 @@ def test_lstm_oracle_matches_reference(kind, golden_dir):
     if kind == "disco":
         np.testing.assert_allclose(a["audio_fea_c"].numpy(), g["audio_fea_c"], atol=1e-5, rtol=0)
         np.testing.assert_allclose(a["audio_fea_r"].numpy(), g["audio_fea_r"], atol=1e-5, rtol=0)
+
+
+def test_oracle_tokenisation_matches_reference(golden_dir):
+    """Training-side tokenisation: EmageVQModel.map2index / map2latent and EmageVQVAEConv.forward
+    of the real reference (tests/golden/make_golden_tokenise.py) vs the oracle restatement."""
+    from oracle import emage_oracle as O
+    from oracle.weights import make_checkpoint
+    g = np.load(os.path.join(golden_dir, "case_tokenise.npz"))
+    _, _, vq = make_checkpoint(seed=0)
+    rot6d, expr = torch.from_numpy(g["rot6d"]), torch.from_numpy(g["expression"])
+    contact, trans = torch.from_numpy(g["tar_contact"]), torch.from_numpy(g["tar_trans"])
+    with torch.no_grad():
+        idx, lat = O.vq_tokenise(vq, rot6d, expr, contact, trans)
+        idx0, _ = O.vq_tokenise(vq, rot6d, expr)
+        parts = O.split_inputs(rot6d, expr, contact, trans)
+        for p in ("face", "upper", "hands", "lower"):
+            assert np.array_equal(parts[p].numpy(), g["input_" + p]), p
+            assert np.array_equal(idx[p].numpy(), g["idx_" + p]) and np.array_equal(idx0[p].numpy(), g["idx_default_" + p]), p
+            assert np.array_equal(lat[p].numpy(), g["latent_" + p]), p
+            fw = O.vqvae_forward(vq, p, parts[p])
+            np.testing.assert_allclose(fw["rec_pose"].numpy(), g["rec_pose_" + p], atol=2e-5, rtol=0)
+            np.testing.assert_allclose(fw["poses_feat"].numpy(), g["poses_feat_" + p], atol=1e-6, rtol=0)
+            np.testing.assert_allclose(float(fw["embedding_loss"]), float(g["embedding_loss_" + p]), rtol=1e-5)
+            np.testing.assert_allclose(float(fw["perplexity"]), float(g["perplexity_" + p]), rtol=1e-5)
+
