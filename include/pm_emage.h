@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 2
+#define PM_ABI_VERSION 3
 #define PM_FMT_F16 0x100
 int pm_abi_version(void);
 /* compute capability major*10+minor of the current device, or <0 */
@@ -118,15 +118,26 @@ int pm_window_input_f32(const float* motion, const float* mask, const float* see
                         uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- VQ ------------------------------------------------------------------------------------------ */
-/* index = argmin_k ( |z|^2 + |e_k|^2 - 2 z.e_k ), first minimum wins: EmageVQVAEConv.decode_from_latent
- * M.py:60-65, Quantizer.map2index P.py:158-164.  e_dim must be 256, n_codes a multiple of 64.
- * e2 = precomputed |e_k|^2 (n_codes).  Writes int64 indices. */
+/* index = argmin_k ( |z|^2 + |e_k|^2 - 2 z.e_k ) evaluated in fp32, first minimum wins (a row of NaNs yields 0, like
+ * torch.argmin): EmageVQVAEConv.decode_from_latent M.py:60-65, Quantizer.map2index P.py:158-164.
+ * e2 = precomputed |e_k|^2 (n_codes).  Writes int64 indices.  e_dim must be 256.
+ *   pm_l2_argmin_tc      n_codes == 256: persistent tcgen05 kernel - fp16 UMMA screen of all 256 scores per row with a
+ *                        rigorous error bound, exact fp32 re-scoring of every row whose best two screened distances
+ *                        are within that bound; each z row is read from HBM once (1 KB + 8 B written per row).
+ *                        max_ctas > 0 caps the persistent grid (<= 0: one CTA per SM).
+ *   pm_l2_argmin_simt_f32  n_codes a multiple of 64: register-tiled fp32 SIMT kernel (sequential-k fp32 FMA).
+ *   pm_l2_argmin_f32     dispatcher the product calls: tc for 256-code codebooks, simt otherwise. */
 int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
                      int n_codes, int e_dim, long long* index, void* stream);
+int pm_l2_argmin_tc(const float* z, long long rows, const float* codebook, const float* e2,
+                    int n_codes, int e_dim, long long* index, int max_ctas, void* stream);
+int pm_l2_argmin_simt_f32(const float* z, long long rows, const float* codebook, const float* e2,
+                          int n_codes, int e_dim, long long* index, void* stream);
 /* index = first argmax over the last dim: torch.max(F.log_softmax(x,2),2)[1], M.py:398-401 (monotone). */
 int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream);
-/* out[r,:] = codebook[index[r],:]: Quantizer.get_codebook_entry P.py:166-170 */
-int pm_gather_rows_f32(const float* codebook, const long long* index, long long rows, int ch,
+/* out[r,:] = codebook[index[r],:]: Quantizer.get_codebook_entry P.py:166-170, nn.Embedding M.py:285-286.
+ * n_table = rows of `codebook`; indices outside [0, n_table) are clamped (never an out-of-bounds read). */
+int pm_gather_rows_f32(const float* codebook, long long n_table, const long long* index, long long rows, int ch,
                        float* out, uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 /* |e_k|^2 per codebook row (done once at pack time) */
 int pm_row_sqnorm_f32(const float* x, int rows, int ch, float* out, void* stream);

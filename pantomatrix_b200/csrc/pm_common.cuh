@@ -23,6 +23,16 @@
 
 static inline int pm_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: one bit per device ordinal, kept by each call site.
+// True when the current device has not been configured through `mask` yet (idempotent, so a race only repeats the call).
+static inline bool pm_first_use_on_device(unsigned long long& mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+  if ((mask >> d) & 1ull) return false;
+  mask |= 1ull << d;
+  return true;
+}
+
 enum PmAct { PM_ACT_NONE = 0, PM_ACT_RELU = 1, PM_ACT_LEAKY = 2 };
 
 __device__ __forceinline__ float pm_act(float v, int act, float slope) {
@@ -66,6 +76,11 @@ __device__ __forceinline__ void pm_split3(float v, __nv_bfloat16 (&p)[3]) {
 #ifndef PM_FMT_F16
 #define PM_FMT_F16 0x100
 #endif
+// fp16 activation planes hold PM_F16_ACT_SCALE * x.  Measured on B200 (round 2): tcgen05.mma kind::f16 FLUSHES fp16
+// subnormal operands, so the second plane of an element below 2^-3 (|p1| < 2^-14) would be lost; the exact pre-scale
+// moves that threshold to 2^-9 (absolute error <= 2^-21 per element) and the overflow threshold to 65504 / 64 = 1023.
+// The packed weights' acc_scale carries the matching 1 / 64 (ops.PackedW), so GEMM results are unchanged.
+#define PM_F16_ACT_SCALE 64.0f
 // host side: strip the format bit of an `nsplit` ABI argument into a flag
 #define PM_TAKE_FMT(nsplit_var, flag_var)                          \
   const bool flag_var = ((nsplit_var) & PM_FMT_F16) != 0;          \
@@ -77,6 +92,7 @@ template <bool F16>
 __device__ __forceinline__ void pm_store_planes_t(const PmPlanes& P, long long row, int c, float v) {
   if constexpr (F16) {
     __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
+    v *= PM_F16_ACT_SCALE;
     for (int pl = 0; pl < P.nsplit; ++pl) {
       const __half h = __float2half_rn(v);
       o[(long long)pl * P.ps] = h;
@@ -100,6 +116,7 @@ template <bool F16>
 __device__ __forceinline__ void pm_store_planes4_t(const PmPlanes& P, long long row, int c, float4 v) {
   if constexpr (F16) {
     __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
+    v.x *= PM_F16_ACT_SCALE; v.y *= PM_F16_ACT_SCALE; v.z *= PM_F16_ACT_SCALE; v.w *= PM_F16_ACT_SCALE;
     for (int pl = 0; pl < P.nsplit; ++pl) {
       const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
       uint2 w;

@@ -165,11 +165,10 @@ extern "C" int pm_lstm_bidir_f32(const float* xproj, long long x_bs, int ldx, co
   PM_REQUIRE(ldx >= 8 * hidden && ldy >= 2 * hidden && (ldy & 3) == 0 && (y_bs & 3) == 0);
   PM_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(whh) & 15) == 0);
   const size_t smem = (size_t)(4 * UPC + RB) * HID * sizeof(float);       // 192 KB
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (pm_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(lstm_bidir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+    if (e != cudaSuccess) { configured = 0; return (int)e; }
   }
   cudaStream_t st = (cudaStream_t)stream;
   for (int b0 = 0; b0 < batch; b0 += 2 * RB) {         // batch rows are independent: 64 clips (128 CTAs) per launch

@@ -23,9 +23,6 @@
 #include "pm_common.cuh"
 #include "../../include/pm_emage.h"
 
-#if defined(PM_TC_TMA_STORE) && !defined(PM_TC_EPI_PREFETCH)
-#define PM_TC_EPI_PREFETCH 1   // the TMA-store epilogue builds on the prefetching loop structure
-#endif
 
 namespace {
 
@@ -48,11 +45,6 @@ struct TcParams {
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
-  int cm, cn;   // thread-block cluster (cm x cn tiles): W tile multicast across cm, A tile across cn
-  int pdl;      // launched with programmatic stream serialization: prologue overlaps the previous kernel's tail
-#ifdef PM_TC_TMA_STORE
-  int tma_ok;   // output tensor maps are valid for every requested output and the staging fits the operand ring
-#endif
   float acc_scale;   // fp16 operands: weights are packed scaled by a power of two, undone here (1 for bf16)
 };
 
@@ -70,156 +62,12 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 #define PM_STAMP(i) do {} while (0)
 #endif
 
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-// Same, for the hot loops: first probe without touching the clock; the watchdog only runs while actually waiting.
-__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  if (!done) mbar_wait(bar, parity);
-}
-// One lane of a converged warp (PTX elect.sync): the canonical guard for TMA / tcgen05 issue.  With warp-uniform
-// control flow around it the compiler keeps descriptors and barrier addresses in uniform registers; guarding with
-// `lane == 0` instead makes them thread-varying and wraps every UTMALDG / UTCHMMA in a waterfall loop.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// UMMA smem descriptors (cute::UMMA::SmemDescriptor, version 1 = sm_100): K-major, 128-byte swizzle, 8-row groups
-// 1024 B apart; built in the MMA loop as desc_hi | (addr >> 4).
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-#ifdef PM_TC_TMA_STORE
-// Epilogue variant (unmeasured, -DPM_TC_TMA_STORE): results leave through the TMA engine.  Each epilogue warp
-// finishes its 32 x 32 chunk in the TMEM row layout (lane = row), writes it into a swizzled staging tile and one lane
-// issues cp.async.bulk.tensor stores (fp32 tile + one per bf16 plane); out-of-range rows / columns are clipped by
-// the tensor map, so there is no per-element tail code on this path.
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-#endif
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+#include "pm_tc_ptx.cuh"   // PTX wrappers: mbarrier, TMA, tcgen05
 
 // ---------------------------------------------------------------------------------------------------
 template <int BN, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
-#ifdef PM_TC_TMA_STORE
-                                                                    const __grid_constant__ CUtensorMap map_o,
-                                                                    const __grid_constant__ CUtensorMap map_p,
-#endif
                                                                     const TcParams p) {
   constexpr int W_TILE_BYTES = BN * BK * 2;
   // instruction descriptor: D = f32; A and B format field 1 = bf16, 0 = fp16; K-major A and B; N >> 3; M >> 4
@@ -230,7 +78,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   // cross terms apart and halving the chain length of the main sums brings the result back to fp32-FMA quality.
   // The epilogue adds the three in fp32.
   constexpr int TMEM_COLS = BN == 64 ? 256 : 512;   // 3 accumulators rounded up to a power of two
-  constexpr int ACC = BN == 96 ? 128 : BN;          // column stride between the accumulators
+  constexpr int ACC = BN;                           // column stride between the accumulators
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][nsplit A tiles][nsplit W tiles] (1024-aligned), then barriers
@@ -248,21 +96,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
   const int n_iter = p.taps * p.kblocks;
-  // thread-block cluster: CTAs of one cluster share operand tiles through TMA multicast
-  const bool clustered = p.cm * p.cn > 1;
-  const uint32_t crank = clustered ? cluster_ctarank() : 0;
-  const int rx = (int)crank % p.cm, ry = (int)crank / p.cm;
-  uint16_t mask_w = 0, mask_a = 0;                              // CTAs that receive my W slice / my A slice
-  for (int i = 0; i < p.cm; ++i) mask_w |= (uint16_t)(1u << (ry * p.cm + i));
-  for (int j = 0; j < p.cn; ++j) mask_a |= (uint16_t)(1u << (rx + j * p.cm));
-  const uint16_t mask_all = mask_w | mask_a;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), (uint32_t)(p.cm + p.cn - 1));   // every CTA that writes into this stage
+      mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(acc_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -273,18 +113,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (clustered) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) PM_STAMP(1);                                   // prologue done (barriers, TMEM, descriptors)
-  if (p.pdl) {
-    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) ran
-    // while the previous kernel on the stream was still draining.  Let the NEXT kernel start its own prologue as
-    // soon as SMs free up, then wait until the previous kernel's memory is complete and visible before any thread
-    // touches activations (TMA loads, residual reads) or writes outputs.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-  }
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -316,16 +147,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         for (int pl = 0; pl < p.nsplit; ++pl) {
           const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
           const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
-          if (p.cn == 1) tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
-          else {                                   // my 128/cn-row slice of the A tile, to every CTA of my tile row
-            const int ar = BM / p.cn;
-            tma_load_4d_mc(a_dst + ry * ar * 128, &map_a, bar, kb * BK, l0 + tap - p.pad + ry * ar, b0, pl, mask_a);
-          }
-          if (p.cm == 1) tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
-          else {                                   // my BN/cm-row slice of the W tile, to every CTA of my tile column
-            const int wr = BN / p.cm;
-            tma_load_3d_mc(w_dst + rx * wr * 128, &map_w, bar, kb * BK, tap * p.w_rows + n0 + rx * wr, pl, mask_w);
-          }
+          tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+          tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
         }
         }
         __syncwarp();
@@ -379,8 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_main, a0 + k * K_ST, w0 + k * K_ST, IDESC, (k | (int)(first ^ 1u)) != 0);
         }
-        if (clustered) tc_commit_mc(smem_u32(&empty_bar[s]), mask_all);   // free the stage in every CTA that fills it
-        else tc_commit(smem_u32(&empty_bar[s]));        // frees this smem stage when the MMAs have read it
+        tc_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
         }
         __syncwarp();
         if (p.nsplit >= 2) first_corr = 0;
@@ -400,32 +222,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     // fast path for full chunks.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-#ifndef PM_TC_EPI_PREFETCH
-    mbar_wait(smem_u32(acc_bar), 0);
-    tc_fence_after();
-    if (warp == 2) PM_STAMP(4);                                   // accumulators complete
-#endif
-    // Column chunk per tcgen05.ld: 32, or 16 for the 96-column tile (each warp group owns 48 columns).
-    constexpr int CW = BN == 96 ? 16 : 32;
+    constexpr int CW = 32;                                         // columns per tcgen05.ld chunk
     constexpr int LPR = CW / 4;                                    // lanes per staged row (one float4 each)
     constexpr int RPI = 32 / LPR;                                  // rows written per warp-wide store
     constexpr int NIT = 32 / RPI;                                  // store rounds per chunk
     constexpr int ST = CW + 4;                                     // staging row stride (floats): 16B aligned, conflict-free
-#ifndef PM_TC_TMA_STORE
     const uint32_t stage = smem_u32(tiles) + (warp - 2) * 32 * ST * 4;   // <= 4.6 KB per warp (shared-space address)
-#endif
     const int sub_r = lane / LPR, c4 = (lane % LPR) * 4;           // this lane's row-in-group / first column of its float4
     const int r_shift = 31 - __clz(p.R);                           // R is a power of two
-#ifdef PM_TC_TMA_STORE
-    constexpr int NCH = BN / 2 / CW;                               // chunks per warp, each with its own staging slot
-    constexpr int CHUNK_STAGE = CW == 32 ? 4096 + 3 * 2048 : 3072; // fp32 tile + 3 plane tiles | legacy transpose tile
-    const uint32_t stage_warp = smem_u32(tiles) + (warp - 2) * NCH * CHUNK_STAGE;
-    const int rt_l = q * 32 + lane;                                // this lane's tile row in the TMEM layout
-    const int b_l = b0 + (rt_l >> r_shift), l_l = l0 + (rt_l & (p.R - 1));
-    const bool row_l_ok = b_l < p.batch && l_l < p.rows_out;
-    const long long off_rl = (long long)b_l * p.r_bs + (long long)l_l * p.ldr;
-    bool did_tma = false;
-#endif
     const bool vec_f = p.out_f32 && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) && ((p.o_bs & 3) == 0);
     const bool vec_r = p.residual && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) && ((p.r_bs & 3) == 0);
     const bool vec_b = p.out_bf16 && ((p.ldob & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0) &&
@@ -449,51 +253,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       uint32_t acc[CW];
       float v[CW];
       const uint32_t lane_col = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-#ifdef PM_TC_EPI_PREFETCH
-      // Variant (unmeasured, -DPM_TC_EPI_PREFETCH): everything that does not depend on the accumulators - row
-      // offsets above, this chunk's bias and residual loads - is issued BEFORE the accumulator wait / TMEM loads,
-      // so their global latency overlaps the tail of the mainloop instead of sitting in the epilogue.
+      // Everything that does not depend on the accumulators - row offsets above, this chunk's bias and residual
+      // loads - is issued BEFORE the accumulator wait / TMEM loads, so their global latency overlaps the tail of the
+      // mainloop instead of sitting in the epilogue (measured round 2: 33.4 -> 30.6 ms per step in bf16x6 mode,
+      // 26.5 -> 23.9 ms in fp16x3, profiles/README.md).
       const int nb = n0 + c0;                                                      // first column of this chunk
       const int n = nb + c4;                                                       // this lane's first column
       const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
-#ifdef PM_TC_TMA_STORE
-      const uint32_t stage = stage_warp + ((c0 - half * (BN / 2)) / CW) * CHUNK_STAGE;
-      const bool use_tma = CW == 32 && p.tma_ok && nb + 32 <= p.cout;              // warp-uniform
-      float4 add4[8];                                              // bias of the 32 columns + residual of my row
-      if (use_tma) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          add4[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.residual && row_l_ok) {
-            const float4 t = *reinterpret_cast<const float4*>(p.residual + off_rl + nb + 4 * j);
-            add4[j].x += t.x; add4[j].y += t.y; add4[j].z += t.z; add4[j].w += t.w;
-          }
-        }
-      }
-#else
-      constexpr bool use_tma = false;
-#endif
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!use_tma && p.bias) {
+      if (p.bias) {
         if (n < p.cout) bias4.x = __ldg(p.bias + n);
         if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
         if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
         if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
       }
-#ifndef PM_TC_TMA_STORE                                            // (register budget: the TMA build keeps its own addends)
       float4 rres[NIT];
-      if (!use_tma && fast && p.residual) {
+      if (fast && p.residual) {
 #pragma unroll
         for (int i = 0; i < NIT; ++i)
           rres[i] = ((row_ok >> i) & 1u) ? *reinterpret_cast<const float4*>(p.residual + off_r[i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-#endif
       if (c0 == half * (BN / 2)) {
         mbar_wait(smem_u32(acc_bar), 0);
         tc_fence_after();
         if (warp == 2) PM_STAMP(4);                                 // accumulators complete
       }
-#endif
       __syncwarp();                                                                // .sync.aligned: whole warp converged
       tmem_ld(lane_col, acc);
 #pragma unroll
@@ -512,84 +296,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < CW; ++j) v[j] *= p.acc_scale;
       }
-#ifndef PM_TC_EPI_PREFETCH
-      const int nb = n0 + c0;                                                      // first column of this chunk
-#endif
       if (nb >= p.cout) continue;                                   // warp-uniform
-#ifdef PM_TC_TMA_STORE
-      if (use_tma) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {                               // bias, residual, activation in the row layout
-          const int nj = nb + 4 * j;
-          const float t0 = nj < p.act_cols ? act_slope : 1.f, t1 = nj + 1 < p.act_cols ? act_slope : 1.f;
-          const float t2 = nj + 2 < p.act_cols ? act_slope : 1.f, t3 = nj + 3 < p.act_cols ? act_slope : 1.f;
-          const float x0 = v[4 * j] + add4[j].x, x1 = v[4 * j + 1] + add4[j].y;
-          const float x2 = v[4 * j + 2] + add4[j].z, x3 = v[4 * j + 3] + add4[j].w;
-          v[4 * j] = fmaxf(x0, 0.f) + t0 * fminf(x0, 0.f);
-          v[4 * j + 1] = fmaxf(x1, 0.f) + t1 * fminf(x1, 0.f);
-          v[4 * j + 2] = fmaxf(x2, 0.f) + t2 * fminf(x2, 0.f);
-          v[4 * j + 3] = fmaxf(x3, 0.f) + t3 * fminf(x3, 0.f);
-        }
-        if (p.out_f32) {                                            // [32 rows][128 B], 128-byte swizzle
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(stage + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (p.out_bf16) {
-#pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {
-            if (pl >= p.out_nsplit) break;
-            const uint32_t st_p = stage + 4096 + pl * 2048;         // [32 rows][64 B], 64-byte swizzle
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                if constexpr (F16) {
-                  const __half2 t = __floats2half2_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
-                  w[h] = *reinterpret_cast<const uint32_t*>(&t);
-                  v[8 * j + 2 * h] -= __low2float(t);
-                  v[8 * j + 2 * h + 1] -= __high2float(t);
-                } else {
-                  const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * h], v[8 * j + 2 * h + 1]);
-                  w[h] = *reinterpret_cast<const uint32_t*>(&t);
-                  v[8 * j + 2 * h] -= __low2float(t);
-                  v[8 * j + 2 * h + 1] -= __high2float(t);
-                }
-              }
-              sts128u(st_p + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
-            }
-          }
-        }
-        fence_async_smem();                                         // generic-proxy writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          const int rt0 = q * 32;
-          const int bs = b0 + (rt0 >> r_shift), ls = l0 + (rt0 & (p.R - 1));
-          if (p.out_f32) tma_store_3d(&map_o, stage, nb, ls, bs);
-          if (p.out_bf16)
-            for (int pl = 0; pl < p.out_nsplit; ++pl) tma_store_4d(&map_p, stage + 4096 + pl * 2048, nb, ls, bs, pl);
-          tma_store_commit();
-        }
-        did_tma = true;
-        continue;
-      }
-#endif
       // transpose: thread = row -> smem[row][0..CW)
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
-#ifndef PM_TC_EPI_PREFETCH
-      const int n = nb + c4;                                                       // this lane's first column
-      const bool fast = all_vec && nb + CW <= p.cout;                              // warp-uniform: whole chunk inside cout
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) {
-        if (n < p.cout) bias4.x = __ldg(p.bias + n);
-        if (n + 1 < p.cout) bias4.y = __ldg(p.bias + n + 1);
-        if (n + 2 < p.cout) bias4.z = __ldg(p.bias + n + 2);
-        if (n + 3 < p.cout) bias4.w = __ldg(p.bias + n + 3);
-      }
-#endif
       // identity == leaky with slope 1: one branch-free formula for none / relu / leaky / partial activation
       const float s0 = n < p.act_cols ? act_slope : 1.f, s1 = n + 1 < p.act_cols ? act_slope : 1.f;
       const float s2 = n + 2 < p.act_cols ? act_slope : 1.f, s3 = n + 3 < p.act_cols ? act_slope : 1.f;
@@ -603,11 +314,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
           float4 x = lds128(stage + ((RPI * i + sub_r) * ST + c4) * 4);
           x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
           if (p.residual) {
-#if defined(PM_TC_EPI_PREFETCH) && !defined(PM_TC_TMA_STORE)
             const float4 t = rres[i];
-#else
-            const float4 t = *reinterpret_cast<const float4*>(p.residual + off_r[i] + n);
-#endif
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           }
           x.x = fmaxf(x.x, 0.f) + s0 * fminf(x.x, 0.f);
@@ -646,9 +353,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         }
       }
     }
-#ifdef PM_TC_TMA_STORE
-    if (did_tma && lane == 0) tma_store_wait_all();                // staging tiles stay valid until the engine has read them
-#endif
   }
 
   if (warp == 2) PM_STAMP(5);                                     // this warp's share of the epilogue issued
@@ -656,7 +360,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 0) PM_STAMP(6);                                     // all warps done
-  if (clustered) cluster_sync_all();        // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -720,76 +423,21 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-#ifdef PM_TC_TMA_STORE
-bool encode_store_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void* base, int rank,
-                      const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
-  EncodeTiledFn fn = get_encode();
-  if (!fn) return false;
-  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  return fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-struct StoreMaps { CUtensorMap o, p; };
-#define PM_TC_STORE_ARGS , const StoreMaps& sm
-#define PM_TC_STORE_PASS , sm.o, sm.p
-#else
-#define PM_TC_STORE_ARGS
-#define PM_TC_STORE_PASS
-#endif
-
 template <int BN, bool F16>
-int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st PM_TC_STORE_ARGS) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
   int stages = (env_kb * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return PM_EUNSUPPORTED;
   p.stages = stages;
-#ifdef PM_TC_TMA_STORE
-  {   // per-chunk staging slots of all 8 epilogue warps (fp32 tile + 3 plane tiles per 32-column chunk) live in
-      // the operand ring, which is idle by then
-    constexpr int CWh = BN == 96 ? 16 : 32;
-    const size_t need = (size_t)8 * (BN / 2 / CWh) * (CWh == 32 ? 4096 + 3 * 2048 : 3072);
-    if (need > (size_t)stages * stage_bytes) return PM_EUNSUPPORTED;
-    if (BN == 96) p.tma_ok = 0;          // 16-column chunks stay on the st.global path
-  }
-#endif
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;       // per template instantiation, one bit per device
+  if (pm_first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+    if (e != cudaSuccess) { configured = 0; return (int)e; }
   }
-  // PM_TC_PDL=1: programmatic dependent launch (see the kernel prologue).
-  static const bool env_pdl = getenv("PM_TC_PDL") && atoi(getenv("PM_TC_PDL")) != 0;
-  p.pdl = env_pdl ? 1 : 0;
-  if (p.cm * p.cn > 1 || p.pdl) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    unsigned n = 0;
-    if (p.cm * p.cn > 1) {
-      attr[n].id = cudaLaunchAttributeClusterDimension;
-      attr[n].val.clusterDim.x = p.cm;
-      attr[n].val.clusterDim.y = p.cn;
-      attr[n].val.clusterDim.z = 1;
-      ++n;
-    }
-    if (p.pdl) {
-      attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[n].val.programmaticStreamSerializationAllowed = 1;
-      ++n;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16>, ma, mw PM_TC_STORE_PASS, p);
-    return e == cudaSuccess ? PM_OK : (int)e;
-  }
-  tapgemm_tc_kernel<BN, F16><<<grid, NUM_THREADS, smem, st>>>(ma, mw PM_TC_STORE_PASS, p);
+  tapgemm_tc_kernel<BN, F16><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
   PM_LAUNCH_CHECK();
 }
 
@@ -824,18 +472,10 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   int R = 128;
   if (rows_out <= 64 && batch > 1) { R = 16; while (R < rows_out) R <<= 1; }
   const int NB = 128 / R;
-  // N tile: 128 columns unless that leaves most of the 148 SMs idle (the M = 2048 transformer GEMMs), then 64
+  // N tile: 128 columns (64 for narrow outputs).  Measured alternatives that lost and were removed: 64-column tiles for
+  // the M = 2048 GEMMs, 96-column tiles (34.2 vs 33.4 ms per step), 2x2 clusters with TMA multicast (10-25 % slower),
+  // programmatic dependent launch (35.2 vs 34.7 ms): profiles/README.md.
   int BNsel = cout <= 64 ? 64 : 128;
-  static const int env_bn = getenv("PM_TC_BN") ? atoi(getenv("PM_TC_BN")) : 0;      // tuning override: 64 | 128
-  if (BNsel == 128 && env_bn == 64) BNsel = 64;   // measured slower (profiles/gemm_microbench_r1.md): off by default
-  // 96-column tiles: 128 CTAs instead of 96 for the M = 2048, N = 768 trunk GEMMs (N = 1536: 256 instead of 192).
-  // Opt-in (PM_TC_BN=96) until it has been measured; only where it lowers waves x tile width.
-  if (BNsel == 128 && env_bn == 96 && w_rows % 96 == 0) {
-    const long long mt = (long long)pm_cdiv(rows_out, R) * pm_cdiv(batch, NB);
-    const long long w128 = (mt * pm_cdiv(cout, 128) + 147) / 148 * 128, w96 = (mt * pm_cdiv(cout, 96) + 147) / 148 * 96;
-    static const bool force96 = getenv("PM_TC_BN") && strchr(getenv("PM_TC_BN"), 'f');   // "96f": wherever legal (tests)
-    if (w96 < w128 || force96) BNsel = 96;
-  }
   PM_REQUIRE(w_rows % BNsel == 0);
 
   TcParams p;
@@ -850,82 +490,30 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.prefetch = static_cast<const uint8_t*>(prefetch);
   p.prefetch_bytes = prefetch ? prefetch_bytes : 0;
   p.acc_scale = acc_scale;
-  // Thread-block clusters with TMA multicast (W shared across cm row tiles, A across cn column tiles) are
-  // implemented and tested but OFF by default: measured on B200 the mainloop is bound by the tensor pipe and the
-  // per-stage barrier round trip, not by L2->smem traffic, and 2x2 clusters were 10-25 % slower
-  // (profiles/gemm_microbench_r1.md).  PM_TC_CLUSTER="cm,cn" turns them on (R == 128 grids only).
-  {
-    static const char* env_cl = getenv("PM_TC_CLUSTER");
-    int want_m = 1, want_n = 1;
-    if (env_cl) sscanf(env_cl, "%d,%d", &want_m, &want_n);
-    const int gx = pm_cdiv(rows_out, R), gy = pm_cdiv(cout, BNsel);
-    p.cm = (R == 128 && want_m > 1 && gx % want_m == 0 && BNsel % (8 * want_m) == 0) ? want_m : 1;
-    p.cn = (R == 128 && want_n > 1 && gy % want_n == 0) ? want_n : 1;
-  }
-
   CUtensorMap ma, mw;
   {
     const long long bs_el = batch > 1 ? a_bs : (long long)rows_in * lda;
     const long long ps_el = nsplit > 1 ? a_ps : bs_el * batch;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows_in, (cuuint64_t)batch, (cuuint64_t)nsplit};
     cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(R / p.cn), (cuuint32_t)NB, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)R, (cuuint32_t)NB, 1};
     if (!encode_map(&ma, A, 4, dims, strides, box, f16)) return PM_EBADARG;
   }
   {
     const long long ps_el = nsplit > 1 ? w_ps : (long long)taps * w_rows * ldw;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps * w_rows, (cuuint64_t)nsplit};
     cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BNsel / p.cm), 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
     if (!encode_map(&mw, W, 3, dims, strides, box, f16)) return PM_EBADARG;
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
-#ifdef PM_TC_TMA_STORE
-  StoreMaps sm;
-  memset(&sm, 0, sizeof(sm));
-  {
-    const int RB = R < 32 ? R : 32, CB = 32 / RB;       // rows / clips of one warp's 32-row store box
-    bool ok = !getenv("PM_TC_NO_TMA_STORE");
-    ok = ok && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
-    ok = ok && (!residual || ((reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (ldr & 3) == 0 && (batch == 1 || (r_bs & 3) == 0)));
-    if (ok && out_f32) {
-      ok = (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && (ldo & 3) == 0 && (batch == 1 || (o_bs & 3) == 0);
-      if (ok) {
-        const long long bs_el = batch > 1 ? o_bs : (long long)rows_out * ldo;
-        cuuint64_t dims[3] = {(cuuint64_t)cout, (cuuint64_t)rows_out, (cuuint64_t)batch};
-        cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)bs_el * 4};
-        cuuint32_t box[3] = {32, (cuuint32_t)RB, (cuuint32_t)CB};
-        ok = encode_store_map(&sm.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, out_f32, 3, dims, strides, box);
-      }
-    }
-    if (ok && out_bf16) {
-      ok = (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0 && (ldob & 7) == 0 && (batch == 1 || (ob_bs & 7) == 0) &&
-           (out_nsplit == 1 || (ob_ps & 7) == 0);
-      if (ok) {
-        const long long bs_el = batch > 1 ? ob_bs : (long long)rows_out * ldob;
-        const long long ps_el = out_nsplit > 1 ? ob_ps : bs_el * batch;
-        cuuint64_t dims[4] = {(cuuint64_t)cout, (cuuint64_t)rows_out, (cuuint64_t)batch, (cuuint64_t)out_nsplit};
-        cuuint64_t strides[3] = {(cuuint64_t)ldob * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
-        cuuint32_t box[4] = {32, (cuuint32_t)RB, (cuuint32_t)CB, 1};
-        ok = encode_store_map(&sm.p, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                              CU_TENSOR_MAP_SWIZZLE_64B, out_bf16, 4, dims, strides, box);
-      }
-    }
-    p.tma_ok = ok ? 1 : 0;
-  }
-#define PM_TC_SM , sm
-#else
-#define PM_TC_SM
-#endif
   if (f16) {
-    if (BNsel == 64) return launch<64, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
-    if (BNsel == 96) return launch<96, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
-    return launch<128, true>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+    if (BNsel == 64) return launch<64, true>(ma, mw, p, grid, (cudaStream_t)stream);
+    return launch<128, true>(ma, mw, p, grid, (cudaStream_t)stream);
   }
-  if (BNsel == 64) return launch<64, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
-  if (BNsel == 96) return launch<96, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
-  return launch<128, false>(ma, mw, p, grid, (cudaStream_t)stream PM_TC_SM);
+  if (BNsel == 64) return launch<64, false>(ma, mw, p, grid, (cudaStream_t)stream);
+  return launch<128, false>(ma, mw, p, grid, (cudaStream_t)stream);
 }
 
 #ifdef PM_TC_TIMING

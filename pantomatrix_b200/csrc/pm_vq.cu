@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NT) l2_argmin_kernel(
   float best[4];
   int bestk[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) { best[a] = INFINITY; bestk[a] = 0x7fffffff; }
+  for (int a = 0; a < 4; ++a) { best[a] = INFINITY; bestk[a] = 0x7fffffff; }   // 0x7fffffff = nothing yet (NaN rows: see the end)
 
   for (int k0 = 0; k0 < n_codes; k0 += CT) {
     __syncthreads();                                        // previous chunk fully consumed (and z2s visible)
@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(NT) l2_argmin_kernel(
       if (ob < best[a] || (ob == best[a] && ok < bestk[a])) { best[a] = ob; bestk[a] = ok; }
     }
     const long long r = r0 + ti * 4 + a;
-    if (tj == 0 && r < rows) index[r] = bestk[a];
+    // a row whose distances are all NaN never updates bestk: emit 0, the index torch.argmin returns for it
+    if (tj == 0 && r < rows) index[r] = bestk[a] == 0x7fffffff ? 0 : bestk[a];
   }
 }
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict
 }
 
 template <bool F16>
-__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ codebook,
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ codebook, long long n_table,
                                                           const long long* __restrict__ index, long long rows,
                                                           int ch4, float* __restrict__ out, PmPlanes P) {
   const long long total = rows * ch4;
@@ -132,7 +133,9 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ch4;
     const int c4 = (int)(i % ch4);
-    const float4 v = reinterpret_cast<const float4*>(codebook)[index[r] * ch4 + c4];
+    long long k = index[r];                       // out-of-range ids (user input) are clamped: never read outside the table
+    k = k < 0 ? 0 : (k >= n_table ? n_table - 1 : k);
+    const float4 v = reinterpret_cast<const float4*>(codebook)[k * ch4 + c4];
     if (out) reinterpret_cast<float4*>(out)[i] = v;
     if (P.ptr) pm_store_planes4_t<F16>(P, r, c4 * 4, v);
   }
@@ -151,21 +154,29 @@ __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict
 
 }  // namespace
 
-extern "C" int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
-                                int n_codes, int e_dim, long long* index, void* stream) {
+extern "C" int pm_l2_argmin_simt_f32(const float* z, long long rows, const float* codebook, const float* e2,
+                                     int n_codes, int e_dim, long long* index, void* stream) {
   PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
   if (e_dim != ED || n_codes <= 0 || n_codes % CT != 0) return PM_EUNSUPPORTED;
   if (rows == 0) return PM_OK;
-  static bool configured = false;
-  if (!configured) {
+  {   // per device, cheap: no process-wide "configured" flag (a second GPU in the same process needs it too)
     cudaError_t e = cudaFuncSetAttribute(l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kL2Smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
   const long long grid = (rows + RT - 1) / RT;
   PM_REQUIRE(grid <= 0x7fffffffLL);
   l2_argmin_kernel<<<(unsigned)grid, NT, kL2Smem, (cudaStream_t)stream>>>(z, rows, codebook, e2, n_codes, index);
   PM_LAUNCH_CHECK();
+}
+
+extern "C" int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
+                                int n_codes, int e_dim, long long* index, void* stream) {
+  // 256 codes x 256 dims (every EMAGE codebook): tensor-core screen + exact fp32 re-scoring (pm_vq_tc.cu);
+  // other codebook sizes: the fp32 SIMT kernel above.  Both return the fp32 argmin with first-index ties.
+  if (n_codes == 256 && e_dim == 256 && z && codebook && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(codebook) & 15) == 0)
+    return pm_l2_argmin_tc(z, rows, codebook, e2, n_codes, e_dim, index, 0, stream);
+  return pm_l2_argmin_simt_f32(z, rows, codebook, e2, n_codes, e_dim, index, stream);
 }
 
 extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream) {
@@ -175,18 +186,18 @@ extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx
   PM_LAUNCH_CHECK();
 }
 
-extern "C" int pm_gather_rows_f32(const float* codebook, const long long* index, long long rows, int ch,
+extern "C" int pm_gather_rows_f32(const float* codebook, long long n_table, const long long* index, long long rows, int ch,
                                   float* out, uint16_t* planes, long long p_ps, int p_ld, int p_nsplit,
                                   void* stream) {
-  PM_REQUIRE(codebook && index && (out || planes) && rows >= 0 && ch > 0 && (ch & 3) == 0);
+  PM_REQUIRE(codebook && index && (out || planes) && rows >= 0 && n_table > 0 && ch > 0 && (ch & 3) == 0);
   PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, true));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
   if (rows == 0) return PM_OK;
   long long g = (rows * (ch >> 2) + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  if (f16) gather_rows_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
-  else gather_rows_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, index, rows, ch >> 2, out, P);
+  if (f16) gather_rows_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, n_table, index, rows, ch >> 2, out, P);
+  else gather_rows_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(codebook, n_table, index, rows, ch >> 2, out, P);
   PM_LAUNCH_CHECK();
 }
 

@@ -1,0 +1,361 @@
+// VQ codebook lookup on the tcgen05 tensor cores: exact fp32 argmin at HBM speed.
+//
+//   index[r] = argmin_k ( |z_r|^2 + |e_k|^2 - 2 z_r.e_k ),  first minimum wins   (M.py:60-65, P.py:158-164)
+//
+// 131 072 FLOP per 1 032-byte row is ~40x above the fp32-FMA ridge, so an exact SIMT kernel sits at a few per cent
+// of HBM bandwidth (pm_vq.cu).  Here the 256 x 256 score matrix of a 128-row tile is one fp16 UMMA chain
+// (screen), and only the rows whose two best screened distances are closer than a RIGOROUS bound on the screen's
+// error are re-scored in exact fp32 (same expression and tie rule as the SIMT kernel).  The emitted index is
+// therefore the fp32 argmin for every row, while each row's 1 KB is read from HBM once.
+//
+// Persistent kernel, one CTA per SM, 416 threads:
+//   warps 0-7   loaders    - coalesced float4 loads of 8 full rows per warp and batch (16 x 16 B in flight per thread),
+//                            per-row max / sum of squares by warp shuffle, power-of-two row scaling into the fp16
+//                            range, fp16 conversion into the 128B-swizzled K-major UMMA layout
+//   warp  8     MMA issuer - 16 x tcgen05.mma (M=128, N=256, K=16) per tile into one of two TMEM accumulators
+//   warps 9-12  epilogue   - tcgen05.ld, screened distances d~ = e2[k] - 2 z.e (row scale folded into the FMA),
+//                            pass 1: minimum, pass 2: every k within tau of it; rows with more than one candidate
+//                            are re-scored in fp32 by the whole warp (8 lanes per candidate, shuffle reduction)
+// The fp16 codebook (128 KB, scaled by a power of two) stays resident in shared memory for the CTA's lifetime.
+//
+// Screen error bound: both operands are rounded to fp16 (relative 2^-11 each, values scaled
+// by exact powers of two so neither overflow nor the subnormal range matters), products are exact, accumulation is
+// fp32: |d~_k - d_k| <= 2 * 2^-10 * 1.01 * |z| |e_k| =: B.  If d_k* is the true minimum then d~_k* <= min d~ + 2B,
+// so the candidate set {k : d~_k <= min d~ + 2B (+ fp32 slack)} always contains it.
+#include "pm_common.cuh"
+#include "pm_tc_ptx.cuh"
+#include "../../include/pm_emage.h"
+
+namespace {
+
+constexpr int ED = 256;                 // e_dim
+constexpr int NC = 256;                 // codes
+constexpr int TM = 128;                 // rows per tile (UMMA M)
+constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 4;      // epilogue = warps 9..12
+constexpr int NTHREADS = 32 * (LOAD_WARPS + 1 + EPI_WARPS);     // 416
+constexpr int KB_A = TM * 128;          // bytes of one 64-channel k-block of the z tile (16 KB)
+constexpr int KB_B = NC * 128;          // ... of the codebook (32 KB)
+constexpr int MAXC = 8;                 // extra candidates kept per row; a full list means "re-score every code"
+constexpr int SLOTS = 4;                // ring of per-tile row info (loaders run at most 2 tiles ahead of the epilogue)
+
+struct Smem {
+  static constexpr int B = 0;                               // fp16 codebook, 4 k-blocks
+  static constexpr int A = B + 4 * KB_B;                    // fp16 z tile, 4 k-blocks
+  static constexpr int E2 = A + 4 * KB_A;                   // float[256]
+  static constexpr int INFO = E2 + NC * 4;                  // float2[SLOTS][TM]: (fma multiplier, tau)
+  static constexpr int CAND = INFO + SLOTS * TM * 8;        // uint8[TM][MAXC]
+  static constexpr int BARS = CAND + TM * MAXC;             // mbarriers
+  static constexpr int N_BARS = 2 + 2 + 2 + SLOTS;          // a_full, a_empty, acc_full[2], acc_empty[2], info_full[SLOTS]
+  static constexpr int MISC = BARS + N_BARS * 8;            // tmem slot, emax
+  static constexpr int TOTAL = MISC + 16;
+};
+
+__device__ __forceinline__ uint32_t sw128(int row, int byte_in_row) {      // offset inside one k-block
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((byte_in_row >> 4) ^ (row & 7)) << 4) | (byte_in_row & 15)));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// exact power of two 2^s as a float, s in [-126, 127]
+__device__ __forceinline__ float pow2i(int s) { return __uint_as_float((uint32_t)(s + 127) << 23); }
+// s such that m * 2^s lies in [2^13, 2^14) for a finite normal m > 0; 0 for zero / subnormal / non-finite m
+__device__ __forceinline__ int scale_exp(float m) {
+  const int ex = (int)(__float_as_uint(m) >> 23) & 0xFF;
+  if (ex == 0 || ex == 255) return 0;
+  int s = 140 - ex;
+  return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
+    const float* __restrict__ z, long long rows, const float* __restrict__ codebook, const float* __restrict__ e2,
+    long long* __restrict__ index) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sm_u = smem_u32(sm);
+  float* e2s = reinterpret_cast<float*>(sm + Smem::E2);
+  float2* info = reinterpret_cast<float2*>(sm + Smem::INFO);
+  uint8_t* cands = sm + Smem::CAND;
+  const uint32_t bars = sm_u + Smem::BARS;
+  const uint32_t a_full = bars, a_empty = bars + 8, acc_full = bars + 16, acc_empty = bars + 32, info_full = bars + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::MISC);
+  float* misc_f = reinterpret_cast<float*>(sm + Smem::MISC + 4);       // [0] = max |e_k|^2
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_tiles = (rows + TM - 1) / TM;
+
+  // ---- prologue: barriers, TMEM, resident codebook ----
+  if (tid == 0) {
+    mbar_init(a_full, LOAD_WARPS);
+    mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, EPI_WARPS); }
+    for (int s = 0; s < SLOTS; ++s) mbar_init(info_full + 8 * s, LOAD_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0) {                       // max |e_k|^2 -> codebook scale and the error bound
+    float m = 0.f;
+    for (int k = lane; k < NC; k += 32) { const float v = __ldg(e2 + k); e2s[k] = v; m = fmaxf(m, v); }
+    m = pm_warp_max(m);
+    if (lane == 0) misc_f[0] = m;
+  }
+  __syncthreads();
+  const float e2max = misc_f[0];
+  const float emax = sqrtf(e2max);
+  const int s_cb = scale_exp(emax);      // every |e_kd| <= emax, so the scaled codebook stays below 2^14
+  {
+    const float sc = pow2i(s_cb);
+    for (int i = tid; i < NC * (ED / 4); i += NTHREADS) {
+      const int k = i >> 6, c4 = i & 63;                              // code row, float4 index within it
+      const float4 v = __ldg(reinterpret_cast<const float4*>(codebook) + i);
+      const int kb = c4 >> 4, byte = (c4 & 15) * 8;
+      sts64(sm_u + Smem::B + kb * KB_B + sw128(k, byte), pack_h2(v.x * sc, v.y * sc), pack_h2(v.z * sc, v.w * sc));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < LOAD_WARPS) {
+    // ===== loaders =====
+    const float bound_c = 2.0f * 0.0009765625f * 1.02f * emax;        // B = bound_c * |z|  (2 * 2^-10 * 1.02 * |e|max)
+    const float inv_cb = pow2i(-s_cb);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const long long r0 = tile * TM;
+      const int slot = it & (SLOTS - 1);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int rb = warp * 16 + half * 8;
+        float4 v[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long g = r0 + rb + j;
+          if (g < rows) {
+            const float4* p = reinterpret_cast<const float4*>(z + g * ED);
+            v[j][0] = ldg_stream4(p + lane);
+            v[j][1] = ldg_stream4(p + 32 + lane);
+          } else {
+            v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float ss[8], mx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a = v[j][0], b = v[j][1];
+          ss[j] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, b.w * b.w)))))));
+          mx[j] = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                        fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+            mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+          }
+        }
+        if (half == 0) mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);  // previous tile's MMAs have read the A tile
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rb + j;
+          const int s = scale_exp(mx[j]);
+          const float sc = pow2i(s);
+          // lane holds channels 4*lane..+3 (k-block lane/16) and 128 + 4*lane..+3 (k-block 2 + lane/16)
+          const int byte = (lane & 15) * 8;
+          const uint32_t dst = sm_u + Smem::A + (lane >> 4) * KB_A + sw128(r, byte);
+          sts64(dst, pack_h2(v[j][0].x * sc, v[j][0].y * sc), pack_h2(v[j][0].z * sc, v[j][0].w * sc));
+          sts64(dst + 2 * KB_A, pack_h2(v[j][1].x * sc, v[j][1].y * sc), pack_h2(v[j][1].z * sc, v[j][1].w * sc));
+          if (lane == j) {
+            // d~ = e2[k] + mult * acc ;  tau = 2 B + fp32 slack (covers the exact path's own rounding and flushes)
+            const float mult = -2.0f * pow2i(-s) * inv_cb;
+            const float tau = 2.0f * bound_c * sqrtf(ss[j]) + 2.4e-7f * 16.f * (ss[j] + e2max);
+            info[slot * TM + r] = make_float2(mult, tau);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a_full); mbar_arrive(info_full + 8 * slot); }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = f32, A = B = f16, K-major, N = 256, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint64_t a_desc = UMMA_DESC_K_SW128 | (uint64_t)(((sm_u + Smem::A) >> 4) & 0x3FFFu);
+    const uint64_t b_desc = UMMA_DESC_K_SW128 | (uint64_t)(((sm_u + Smem::B) >> 4) & 0x3FFFu);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
+      mbar_wait(a_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (uint32_t)buf * NC;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(d, a_desc + (uint64_t)(kb * (KB_A >> 4) + k * 2), b_desc + (uint64_t)(kb * (KB_B >> 4) + k * 2), IDESC,
+                        (uint32_t)((kb | k) != 0));
+        tc_commit(a_empty);
+        tc_commit(acc_full + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM lane quarter = warp % 4, thread = one row of the tile =====
+    const int q = warp & 3;
+    const int trow = q * 32 + lane;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, slot = it & (SLOTS - 1);
+      const long long g = tile * TM + trow;
+      mbar_wait(info_full + 8 * slot, (uint32_t)((it >> 2) & 1));
+      const float2 inf = info[slot * TM + trow];
+      mbar_wait(acc_full + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NC;
+      // pass 1: minimum of the screened distances (first index wins)
+      float m1 = INFINITY;
+      int k1 = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c0, acc);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
+          const float d0 = fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), d1 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y);
+          const float d2 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), d3 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w);
+          if (d0 < m1) { m1 = d0; k1 = c0 + 4 * j4; }
+          if (d1 < m1) { m1 = d1; k1 = c0 + 4 * j4 + 1; }
+          if (d2 < m1) { m1 = d2; k1 = c0 + 4 * j4 + 2; }
+          if (d3 < m1) { m1 = d3; k1 = c0 + 4 * j4 + 3; }
+        }
+      }
+      // pass 2: every other code within tau of the minimum
+      const float thr = m1 + inf.y;
+      int nc = 0;
+      uint8_t* my = cands + trow * MAXC;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c0, acc);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
+          const float d[4] = {fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y),
+                              fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w)};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = c0 + 4 * j4 + u;
+            if (d[u] <= thr && k != k1) {
+              if (nc < MAXC) my[nc] = (uint8_t)k;
+              ++nc;
+            }
+          }
+        }
+      }
+      // accumulator drained: hand it back to the MMA warp before the (rare, slow) exact re-scoring
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+
+      // ---- exact fp32 re-scoring of rows with more than one candidate: whole warp per row, 8 lanes per code ----
+      unsigned need = __ballot_sync(0xffffffffu, nc > 0 && g < rows);
+      const int grp = lane >> 3, gl = lane & 7;
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int nsrc = __shfl_sync(0xffffffffu, nc, src);
+        const int ksrc = __shfl_sync(0xffffffffu, k1, src);
+        const bool all = nsrc > MAXC;                                    // list overflowed: every code is a candidate
+        const int ncand = all ? NC : nsrc + 1;
+        const long long gr = tile * TM + q * 32 + src;
+        const float4* zr = reinterpret_cast<const float4*>(z + gr * ED);
+        float4 zv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zv[i] = __ldg(zr + gl + 8 * i);
+        float z2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z2 = fmaf(zv[i].x, zv[i].x, fmaf(zv[i].y, zv[i].y, fmaf(zv[i].z, zv[i].z, fmaf(zv[i].w, zv[i].w, z2))));
+        z2 += __shfl_xor_sync(0xffffffffu, z2, 1);
+        z2 += __shfl_xor_sync(0xffffffffu, z2, 2);
+        z2 += __shfl_xor_sync(0xffffffffu, z2, 4);
+        float best = INFINITY;
+        int bk = NC;                                                     // NC = "nothing yet" (loses every tie)
+        const uint8_t* list = cands + (q * 32 + src) * MAXC;
+        for (int base = 0; base < ncand; base += 4) {
+          const int ci = base + grp;
+          const bool valid = ci < ncand;
+          const int c = !valid ? ksrc : (all ? ci : (ci == 0 ? ksrc : (int)list[ci - 1]));
+          const float4* er = reinterpret_cast<const float4*>(codebook + (long long)c * ED);
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ev = __ldg(er + gl + 8 * i);
+            dot = fmaf(zv[i].x, ev.x, fmaf(zv[i].y, ev.y, fmaf(zv[i].z, ev.z, fmaf(zv[i].w, ev.w, dot))));
+          }
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          float dd = __fsub_rn(__fadd_rn(z2, e2s[c]), __fmul_rn(2.f, dot));       // the expression of M.py:64
+          int cc = c;
+          if (!valid) { dd = INFINITY; cc = NC; }
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {                                     // combine the four groups
+            const float od = __shfl_xor_sync(0xffffffffu, dd, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, cc, o);
+            if (od < dd || (od == dd && oc < cc)) { dd = od; cc = oc; }
+          }
+          if (dd < best || (dd == best && cc < bk)) { best = dd; bk = cc; }
+        }
+        if (lane == src && bk < NC) k1 = bk;      // all-NaN rows keep the screen's answer (0, like torch.argmin)
+      }
+      if (g < rows) index[g] = (long long)k1;
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+constexpr size_t kSmem = Smem::TOTAL + 1024;
+
+}  // namespace
+
+extern "C" int pm_l2_argmin_tc(const float* z, long long rows, const float* codebook, const float* e2,
+                               int n_codes, int e_dim, long long* index, int max_ctas, void* stream) {
+  PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
+  if (e_dim != ED || n_codes != NC) return PM_EUNSUPPORTED;
+  PM_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
+  if (rows == 0) return PM_OK;
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  static unsigned long long configured = 0;
+  if (pm_first_use_on_device(configured)) {
+    e = cudaFuncSetAttribute(l2_argmin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) { configured = 0; return (int)e; }
+  }
+  const long long tiles = (rows + TM - 1) / TM;
+  long long grid = tiles < sms ? tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  l2_argmin_tc_kernel<<<(unsigned)grid, NTHREADS, kSmem, (cudaStream_t)stream>>>(z, rows, codebook, e2, index);
+  PM_LAUNCH_CHECK();
+}

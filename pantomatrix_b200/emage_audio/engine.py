@@ -46,16 +46,19 @@ def wav_out_len(n: int) -> int:
     return length
 
 
-# Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores
-# with plain bf16 / bf16x3 / bf16x6 split operands (see csrc/pm_tapgemm_tc.cu).
+# Arithmetic engine of every Conv1d / Linear ("tap-GEMM"): 0 = fp32 SIMT kernel, 1/2/3 = tcgen05 tensor cores with
+# 1 / 2 / 3 operand planes (csrc/pm_tapgemm_tc.cu).
+#   fp16x3 (default)  two IEEE fp16 planes (22 mantissa bits), 3 tensor-core products per fp32 product.  Measured on
+#                     B200 (round 2, profiles/README.md): all 38 400 codes of the BASELINE batch identical to the fp32
+#                     reference, latent error 4.3e-4 (bf16x6: 3.8e-4), 24 ms per step against 31 ms.  Operands must stay
+#                     below 65504 / 64 (activations are pre-scaled by 64, ops.F16_ACT_SCALE): pipeline.py checks the
+#                     outputs for the NaN an overflow would leave and names bf16x6 as the way out.
+#   bf16x6            three bf16 planes, 6 products: same accuracy, no range limit (fp32 exponent range), 1.3x slower.
+#   bf16x3 / bf16     faster, below the parity gates (measured agreement in profiles/README.md).
+#   fp32              exact-order fp32 SIMT engine (reference engine of the tests).
 PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3, "fp16x3": 2}
-# "fp16x3" (experimental, not yet measured on hardware): two IEEE fp16 planes, 3 products - the accuracy of bf16x6
-# at the cost of bf16x3 while activations stay below 65504 (profiles/split_formats_r1.json); pipeline.py checks the
-# outputs for the NaN an overflow would leave.
 PLANE_FORMAT = {"fp16x3": "fp16"}
-# Default: bf16x6 - the tensor-core mode that meets the fp32 parity gates.  "fp32" selects the
-# exact-order SIMT engine, "bf16x3" / "bf16" trade accuracy for speed.  PM_EMAGE_PRECISION overrides the default.
-DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "bf16x6")
+DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "fp16x3")     # PM_EMAGE_PRECISION overrides
 _STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True,   # fork: overlap independent branches on side streams
           "precision": DEFAULT_PRECISION}
 ops.set_plane_format(PLANE_FORMAT.get(DEFAULT_PRECISION, "bf16"))

@@ -21,6 +21,9 @@ launch_count = 0
 # Element format of the tensor-core operand planes: bf16 (default) or IEEE fp16.  Two fp16 planes (3 products)
 # match three bf16 planes (6 products) in accuracy while magnitudes stay below 65504 (include/pm_emage.h).
 FMT_F16 = 0x100
+# fp16 activation planes hold F16_ACT_SCALE * x (csrc/pm_common.cuh PM_F16_ACT_SCALE: the tensor core flushes fp16
+# subnormal operands, the exact pre-scale keeps second planes normal down to |x| = 2^-9); PackedW.acc_scale undoes it.
+F16_ACT_SCALE = 64.0
 _PLANE_DTYPE = torch.bfloat16
 
 
@@ -208,13 +211,23 @@ def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit
     return _result(out, pl, nsplit)
 
 
-def l2_argmin(z, codebook, e2):
+def l2_argmin(z, codebook, e2, engine="auto", max_ctas=0):
+    """fp32 argmin_k |z - e_k|^2, first minimum wins.  engine: "auto" (the product path: tcgen05 screen + exact fp32
+    re-scoring for 256-code codebooks, fp32 SIMT otherwise), "tc" or "simt" (tests / microbenchmarks)."""
     _chk(z), _chk(codebook), _chk(e2)
     assert z.is_contiguous() and codebook.is_contiguous()
     rows = z.numel() // z.shape[-1]
     idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
-    _call("pm_l2_argmin_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), codebook.shape[0],
-          codebook.shape[1], idx.data_ptr(), _stream())
+    n_codes, e_dim = codebook.shape
+    if engine == "tc":
+        _call("pm_l2_argmin_tc", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim, idx.data_ptr(),
+              int(max_ctas), _stream())
+    elif engine == "simt":
+        _call("pm_l2_argmin_simt_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim,
+              idx.data_ptr(), _stream())
+    else:
+        _call("pm_l2_argmin_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim, idx.data_ptr(),
+              _stream())
     return idx
 
 
@@ -236,7 +249,8 @@ def gather_rows(codebook, index, nsplit=0, f32=True):
     if nsplit:
         lead = (index.shape[0], index.numel() // index.shape[0]) if index.dim() > 1 else (1, index.numel())
         pl = _new_planes(nsplit, lead, ch, codebook.device)
-    _call("pm_gather_rows_f32", codebook.data_ptr(), index.data_ptr(), index.numel(), ch, _ptr(out), *_pargs(pl), _stream())
+    _call("pm_gather_rows_f32", codebook.data_ptr(), codebook.shape[0], index.data_ptr(), index.numel(), ch, _ptr(out),
+          *_pargs(pl), _stream())
     return _result(out, pl, nsplit)
 
 
@@ -319,7 +333,7 @@ def split_bf16(x, nsplit, slack_rows=0):
 class PackedW:
     """Weights of one tap-GEMM for the tensor-core engine: (nsplit, taps, w_rows, ldw) bf16 (or fp16) planes.
     fp16 planes hold W * 2^k with the largest |W| in [16384, 32768) - small weights keep their second plane out of
-    the fp16 subnormals - and `acc_scale` = 2^-k is handed to the kernel's epilogue."""
+    the fp16 subnormals - and `acc_scale` = 2^-k / F16_ACT_SCALE is handed to the kernel's epilogue."""
     __slots__ = ("t", "taps", "cout", "cin", "w_rows", "ldw", "acc_scale")
 
     def __init__(self, w, nsplit):
@@ -337,6 +351,7 @@ class PackedW:
                 k = math.floor(math.log2(32768.0 / m))
                 full = full * (2.0 ** k)
                 self.acc_scale = 2.0 ** -k
+            self.acc_scale /= F16_ACT_SCALE                  # activation planes arrive pre-scaled (exact power of two)
         planes, rem = [], full
         for _ in range(nsplit):                       # round-to-nearest-even, same as the device split
             p = rem.to(_PLANE_DTYPE)

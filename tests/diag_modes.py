@@ -27,7 +27,7 @@ def main():
     want_face = O.l2_argmin(want_lat["rec_face"], vq["face"][0]["quantizer.embedding.weight"])
     model, vqm = build_product(0)
     out = {"clips": bs, "frames": int(want["motion_axis_angle"].shape[1]), "modes": {}}
-    modes = ("fp32", "bf16x6", "bf16x3", "bf16") + (("fp16x3",) if os.environ.get("PM_TEST_EXPERIMENTAL") == "1" else ())
+    modes = ("fp32", "fp16x3", "bf16x6", "bf16x3", "bf16")
     for mode in modes:
         engine.set_precision(mode)
         lat, pred = generate(model, vqm, audio.cuda())

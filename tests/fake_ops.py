@@ -35,7 +35,8 @@ def _mk_planes(y, nsplit, slack_rows=0):
     ld = _round_up(ch, 8)
     buf = torch.full((nsplit, batch * rows + slack_rows, ld), float("nan"), dtype=_plane_dtype())
     buf[:, batch * rows:] = 0
-    for i, p in enumerate(_split(y.reshape(batch * rows, ch).float(), nsplit)):
+    pre = _real.F16_ACT_SCALE if _plane_dtype() == torch.float16 else 1.0      # same exact pre-scale as the kernels
+    for i, p in enumerate(_split(y.reshape(batch * rows, ch).float() * pre, nsplit)):
         buf[i, :batch * rows, :ch] = p
     return Planes(buf[:, :batch * rows].view(nsplit, batch, rows, ld), rows, ch, slack_rows)
 
@@ -109,7 +110,7 @@ def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit
     return _res(torch.where(wk == 1, mask_embedding.view(1, 1, -1).expand_as(wm), wm), nsplit, f32)
 
 
-def l2_argmin(z, codebook, e2):
+def l2_argmin(z, codebook, e2, engine="auto", max_ctas=0):
     flat = z.reshape(-1, codebook.shape[1])
     d = (flat ** 2).sum(1, keepdim=True) + e2 - 2 * flat @ codebook.t()
     return d.argmin(1).reshape(z.shape[:-1])

@@ -11,7 +11,7 @@ import torch
 
 from oracle import emage_oracle as O
 from oracle.weights import make_checkpoint, synth_audio
-from helpers import EXPERIMENTAL, build_product, geodesic_deg
+from helpers import build_product, geodesic_deg
 
 pytestmark = pytest.mark.gpu
 PARTS = ("face", "upper", "hands", "lower")
@@ -28,7 +28,7 @@ def product():
 @pytest.fixture(autouse=True)
 def _exact_engine_by_default():
     """Tests run on the exact-order fp32 engine unless they select a tensor-core mode themselves (the product
-    default is bf16x6; it is exercised by the `precision` parametrisations below)."""
+    default is fp16x3; it is exercised by the `precision` parametrisations below)."""
     from pantomatrix_b200.emage_audio import engine
     engine.set_precision("fp32")
     yield
@@ -88,7 +88,7 @@ def _face_ties(vqm, vq, lat, want_lat, tag, max_ties=0):
     return ~near
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x6", pytest.param("fp16x3", marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x6", "fp16x3"])
 @pytest.mark.parametrize("case", GOLDEN)
 def test_matches_reference_golden(case, precision, product, golden_dir):
     from pantomatrix_b200.emage_audio import engine
@@ -196,7 +196,7 @@ def test_teacher_forced_windows_and_free_run_vs_oracle(product, ckpt):
                  frames=None if ok.all() else ok, raw=want_pred["_raw"])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x6", pytest.param("fp16x3", marks=EXPERIMENTAL)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x6", "fp16x3"])
 def test_baseline_config_batch32(product, ckpt, precision):
     """BASELINE configs[1]: 32 clips x 300 frames, free-running, for the exact fp32 engine and the default
     tensor-core mode.  Index agreement must be total on this seeded input; size-independent properties:
@@ -229,7 +229,7 @@ def test_baseline_config_batch32(product, ckpt, precision):
 
 
 @pytest.mark.parametrize("precision,rec_tol,min_agree", [("bf16x6", 1e-3, 0.9995), ("bf16x3", 2e-2, 0.99), ("bf16", 1.0, 0.80),
-                                                         pytest.param("fp16x3", 1e-3, 0.9995, marks=EXPERIMENTAL)])
+                                                         ("fp16x3", 1e-3, 0.9995)])
 def test_tensor_core_precision_modes(product, ckpt, precision, rec_tol, min_agree):
     """The tcgen05 engine end to end (teacher-forced single windows, so a flipped code cannot cascade):
     bf16x6 must meet the fp32 gate; bf16x3 / bf16 report their agreement and must stay above a floor."""
@@ -260,7 +260,6 @@ def test_tensor_core_precision_modes(product, ckpt, precision, rec_tol, min_agre
     assert same / total >= min_agree, (precision, same, total)
 
 
-@EXPERIMENTAL
 def test_tokenisation_matches_reference_golden(product, golden_dir):
     """map2index / map2latent / EmageVQVAEConv.forward on the GPU against the real reference's outputs
     (tests/golden/case_tokenise.npz); the CPU twin is tests/test_host_logic.py."""

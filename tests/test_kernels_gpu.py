@@ -153,10 +153,14 @@ def _fp64_margins(z, cb):
     return top.indices[:, 0], top.values[:, 1] - top.values[:, 0]
 
 
-@pytest.mark.parametrize("rows", [1, 63, 9600])
-def test_l2_argmin_bit_exact(ops, rows):
+ENGINES = ["tc", "simt"]          # tcgen05 screen + exact fp32 re-scoring (the product path) | fp32 SIMT kernel
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("rows", [1, 63, 9600, 128 * 148 * 2 + 77])
+def test_l2_argmin_bit_exact(ops, rows, engine):
     z, cb = _rand(rows, 256, seed=31), _rand(256, 256, seed=32)
-    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb))
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb), engine=engine)
     want, margin = _fp64_margins(z, cb)
     decided = margin > 1e-3          # fp32 evaluation of d (|d| ~ 500) cannot order closer pairs reliably
     assert decided.float().mean() > 0.99
@@ -164,14 +168,71 @@ def test_l2_argmin_bit_exact(ops, rows):
     # the undecided rows must still pick one of the two near-tied codes
     d32 = (z ** 2).sum(1, keepdim=True) + (cb ** 2).sum(1) - 2 * z @ cb.t()
     assert bool(((d32.gather(1, got[:, None])[:, 0] - d32.min(1).values).abs() < 1e-2).all())
+    if rows == 9600:                 # the dispatcher the product calls picks the tensor-core kernel for 256 codes
+        assert torch.equal(ops.l2_argmin(z, cb, ops.row_sqnorm(cb)), ops.l2_argmin(z, cb, ops.row_sqnorm(cb), engine="tc"))
 
 
-def test_l2_argmin_ties_pick_first(ops):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_l2_argmin_ties_pick_first(ops, engine):
     cb = _rand(256, 256, seed=33)
     cb[200] = cb[7]                                   # duplicate code: lower index must win (torch.argmin)
     z = cb[[7, 200, 9]].clone() + 1e-3
-    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb))
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb), engine=engine)
     assert got.tolist() == [7, 7, 9]
+
+
+@pytest.mark.parametrize("zs,cs", [(1e-6, 1.0), (3e4, 1.0), (1.0, 2e3), (1e-3, 1e-4), (1e9, 1e-9)])
+def test_l2_argmin_tc_any_scale(ops, zs, cs):
+    """The fp16 screen scales rows and codebook by exact powers of two: results do not depend on the data's scale
+    (3e4 * N(0,1) overflows fp16 unscaled, 1e-6 would vanish in its subnormals)."""
+    z, cb = _rand(4099, 256, seed=43, scale=zs), _rand(256, 256, seed=44, scale=cs)
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb), engine="tc")
+    want, margin = _fp64_margins(z, cb)
+    dscale = float((z.double() ** 2).sum(1).mean() + (cb.double() ** 2).sum(1).mean())
+    decided = margin > 2e-6 * dscale
+    assert decided.float().mean() > 0.97
+    assert torch.equal(got[decided], want[decided])
+
+
+def test_l2_argmin_tc_near_ties_are_rescored_exactly(ops):
+    """Rows placed (almost) on the bisector of two codes: the fp16 screen cannot order them, the fp32 re-scoring must.
+    The tensor-core kernel has to agree with the fp32 SIMT kernel wherever fp32 itself can decide."""
+    cb = _rand(256, 256, seed=45)
+    g = torch.Generator().manual_seed(46)
+    a, b = torch.randint(0, 256, (2, 20000), generator=g)
+    eps = (torch.rand(20000, generator=g) - 0.5).cuda() * 2e-5          # offset from the bisector: d_a - d_b ~ +-0.01
+    z = 0.5 * (cb[a.cuda()] + cb[b.cuda()]) + eps[:, None] * (cb[a.cuda()] - cb[b.cuda()])
+    e2 = ops.row_sqnorm(cb)
+    tc, simt = ops.l2_argmin(z, cb, e2, engine="tc"), ops.l2_argmin(z, cb, e2, engine="simt")
+    want, margin = _fp64_margins(z, cb)
+    decided = margin > 2e-3
+    assert 0.5 < decided.float().mean() < 0.999                           # the case really is near-tied
+    assert torch.equal(tc[decided], want[decided]) and torch.equal(simt[decided], want[decided])
+    d64 = (z.double() ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1) - 2 * z.double() @ cb.double().t()
+    assert bool((d64.gather(1, tc[:, None])[:, 0] - d64.min(1).values < 2e-3).all())
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_l2_argmin_nan_and_clustered_rows(ops, engine):
+    """A NaN latent yields index 0 (what torch.argmin returns for an all-NaN row), never an out-of-range index
+    (ADVICE r1); a codebook of near-duplicates makes every code a candidate (the re-score-everything path)."""
+    cb = _rand(256, 256, seed=47)
+    z = _rand(300, 256, seed=48)
+    z[5, 17] = float("nan")
+    z[131] = float("nan")
+    z[200] = 0.0
+    got = ops.l2_argmin(z, cb, ops.row_sqnorm(cb), engine=engine)
+    assert got[5].item() == 0 and got[131].item() == 0
+    assert int(got.min()) >= 0 and int(got.max()) < 256
+    want, margin = _fp64_margins(z.nan_to_num(0.0), cb)
+    ok = (margin > 1e-3) & ~torch.isnan(z).any(1)
+    assert torch.equal(got[ok], want[ok])
+    base = _rand(1, 256, seed=49)
+    cbc = (base + 1e-3 * _rand(256, 256, seed=50)).contiguous()           # 256 codes within 1e-3 of each other
+    zc = (base + 1e-3 * _rand(500, 256, seed=51)).contiguous()
+    gotc = ops.l2_argmin(zc, cbc, ops.row_sqnorm(cbc), engine=engine)
+    d64 = ((zc.double()[:, None, :] - cbc.double()[None]) ** 2).sum(-1)
+    assert bool((d64.gather(1, gotc[:, None])[:, 0] - d64.min(1).values < 5e-4).all())      # fp32 noise of d ~ 512 * 2^-23
 
 
 def test_l2_argmin_million_rows_optimality(ops):
@@ -201,6 +262,10 @@ def test_gather_rows(ops):
     cb = _rand(256, 256, seed=37)
     idx = torch.randint(0, 256, (4, 33), generator=torch.Generator().manual_seed(38)).cuda()
     assert torch.equal(ops.gather_rows(cb, idx), cb[idx])
+    bad = idx.clone()
+    bad[0, 0], bad[1, 1] = 2147483647, -5              # out-of-range ids are clamped, never read out of bounds
+    got = ops.gather_rows(cb, bad)
+    assert torch.equal(got[0, 0], cb[255]) and torch.equal(got[1, 1], cb[0]) and torch.equal(got[2], cb[idx[2]])
 
 
 def test_pose_compose_matches_oracle(ops):
@@ -246,7 +311,9 @@ def test_global_trans_sequential_sum(ops):
 
 
 def _planes_value(pl):
-    return pl.t[:, :, :, :pl.ch].float().sum(0)
+    """fp32 value the planes stand for (fp16 planes hold ops.F16_ACT_SCALE * x)."""
+    from pantomatrix_b200 import ops as o
+    return pl.t[:, :, :, :pl.ch].float().sum(0) / (o.F16_ACT_SCALE if pl.t.dtype == torch.float16 else 1.0)
 
 
 @pytest.fixture()
@@ -256,7 +323,7 @@ def plane_format(request, ops):
     ops.set_plane_format("bf16")
 
 
-@pytest.mark.parametrize("plane_format", ["bf16", pytest.param("fp16", marks=EXPERIMENTAL)], indirect=True)
+@pytest.mark.parametrize("plane_format", ["bf16", "fp16"], indirect=True)
 @pytest.mark.parametrize("nsplit", [1, 2, 3])
 def test_fused_plane_outputs(ops, nsplit, plane_format):
     """Producers that write their result directly as split planes (the A-operand format of the tensor-core

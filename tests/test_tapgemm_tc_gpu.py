@@ -7,7 +7,6 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import EXPERIMENTAL  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -70,6 +69,8 @@ def _run_case(ops, case, nsplit, tol, plane_bits=8):
     err = (got.double() - want).abs().max().item()
     assert err <= tol * scale, f"nsplit={nsplit}: max err {err:.3e} > {tol * scale:.3e}"
     rebuilt = planes.t[:, :, :, :cout].float().sum(0)          # the emitted planes re-assemble the fp32 result
+    if planes.t.dtype == torch.float16:
+        rebuilt = rebuilt / ops.F16_ACT_SCALE                  # fp16 planes hold 64 * x (exact)
     assert (rebuilt - got).abs().max().item() <= max(2.0 ** (-plane_bits * nsplit), 2.0 ** -24) * scale * 1.01
 
 
@@ -79,7 +80,6 @@ def test_tapgemm_tc_matches_fp64(ops, case, nsplit):
     _run_case(ops, case, nsplit, TOL[nsplit])
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize("case", CASES)
 def test_tapgemm_tc_fp16_planes(ops, case):
     """Two IEEE fp16 planes, 3 products: the accuracy class of bf16x6 (weights packed pre-scaled by a power of two,
@@ -124,32 +124,19 @@ def test_strided_conv_as_reshaped_stride1(ops, C, cout):
     _check(got, want, 3, float(want.abs().max()))
 
 
-@EXPERIMENTAL
-def test_bn96_tiles_in_subprocess():
-    """The same parity cases with PM_TC_BN=96f (96-column tiles wherever the packed weights allow).  The knob is read
-    once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, PM_TC_BN="96f", PM_TEST_EXPERIMENTAL="0")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:]
-
-
-@EXPERIMENTAL
-def test_fp16_planes_keep_subnormal_second_plane(ops):
-    """fp16x3 leaves activations unscaled, so small activations put their SECOND plane into the fp16 subnormal range.
-    The CPU study (profiles/split_formats_r1.json) shows the mode collapses to bf16x3 quality or worse if those were
-    flushed to zero; this pins that the tensor core honours fp16 subnormal operands (else: scale the activations)."""
+@pytest.mark.parametrize("scale,tol", [(1.0, 5e-6), (0.05, 5e-6), (1e-3, 3e-4)])
+def test_fp16_planes_small_activations(ops, scale, tol):
+    """Measured on B200 (round 2): tcgen05.mma kind::f16 flushes fp16 SUBNORMAL operands, so the second plane of an
+    element is lost once it drops below 2^-14.  Activation planes are therefore pre-scaled by 64 (exact): LayerNorm-sized
+    and 20x smaller activations keep the fp32-class accuracy; only tensors that are tiny as a whole (1e-3) degrade to
+    single-plane fp16 accuracy (2^-11) - no tensor of this model is that small (smallest GEMM input: ~0.05)."""
     ops.set_plane_format("fp16")
     try:
-        x = _rand(1, 256, 768, seed=11, scale=1e-3)               # second plane ~ 2^-12 * 1e-3 = 2.4e-7: subnormal
+        x = _rand(1, 256, 768, seed=11, scale=scale)
         w = _rand(1, 256, 768, seed=12, scale=1 / math.sqrt(768))
         want = F.linear(x.double(), w[0].double())
         got, _ = ops.tapgemm_tc(ops.split_bf16(x, 2), ops.PackedW(w, 2), None, rows_out=256)
         err = (got.double() - want).abs().max().item()
-        assert err <= TOL[3] * float(want.abs().max()), err
+        assert err <= tol * float(want.abs().max()), err
     finally:
         ops.set_plane_format("bf16")
-
