@@ -38,6 +38,24 @@ constexpr int KB_B = NC * 128;          // ... of the codebook (32 KB)
 constexpr int MAXC = 8;                 // extra candidates kept per row; a full list means "re-score every code"
 constexpr int SLOTS = 4;                // ring of per-tile row info (loaders run at most 2 tiles ahead of the epilogue)
 
+// Instrumented build only (-DPM_VQ_TIMING, tools/vq_timeline.py): clock64 cycles CTA 0 spends per phase.
+#ifdef PM_VQ_TIMING
+__device__ unsigned long long pm_vq_stamps[16];
+#define VQ_T(var) const long long var = clock64()
+#define VQ_ADD(i, t0)                                                                                     \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&pm_vq_stamps[i], (unsigned long long)(clock64() - (t0))); \
+  } while (0)
+#define VQ_CNT(i, n)                                                                                      \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&pm_vq_stamps[i], (unsigned long long)(n)); \
+  } while (0)
+#else
+#define VQ_T(var) do {} while (0)
+#define VQ_ADD(i, t0) do {} while (0)
+#define VQ_CNT(i, n) do {} while (0)
+#endif
+
 struct Smem {
   static constexpr int B = 0;                               // fp16 codebook, 4 k-blocks
   static constexpr int A = B + 4 * KB_B;                    // fp16 z tile, 4 k-blocks
@@ -86,6 +104,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (rows + TM - 1) / TM;
+  VQ_T(t_kernel);
 
   // ---- prologue: barriers, TMEM, resident codebook ----
   if (tid == 0) {
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int rb = warp * 16 + half * 8;
+        VQ_T(t_ld);
         float4 v[8][2];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -163,7 +183,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
             mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
           }
         }
+        if (warp == 0) VQ_ADD(0, t_ld);
+        VQ_T(t_we);
         if (half == 0) mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);  // previous tile's MMAs have read the A tile
+        if (warp == 0) VQ_ADD(1, t_we);
+        VQ_T(t_cv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = rb + j;
@@ -181,6 +205,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
             info[slot * TM + r] = make_float2(mult, tau);
           }
         }
+        if (warp == 0) VQ_ADD(2, t_cv);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -195,8 +220,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
+      VQ_T(t_m0);
       mbar_wait(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
+      VQ_ADD(3, t_m0);
+      VQ_T(t_m1);
       mbar_wait(a_full, (uint32_t)(it & 1));
+      VQ_ADD(4, t_m1);
+      VQ_CNT(11, 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)buf * NC;
@@ -219,10 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1, slot = it & (SLOTS - 1);
       const long long g = tile * TM + trow;
+      VQ_T(t_e0);
       mbar_wait(info_full + 8 * slot, (uint32_t)((it >> 2) & 1));
       const float2 inf = info[slot * TM + trow];
       mbar_wait(acc_full + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (warp == MMA_WARP + 1) VQ_ADD(6, t_e0);
+      VQ_T(t_e1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NC;
       // pass 1: minimum of the screened distances (first index wins)
       float m1 = INFINITY;
@@ -242,6 +275,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
           if (d3 < m1) { m1 = d3; k1 = c0 + 4 * j4 + 3; }
         }
       }
+      if (warp == MMA_WARP + 1) VQ_ADD(7, t_e1);
+      VQ_T(t_e2);
       // pass 2: every other code within tau of the minimum
       const float thr = m1 + inf.y;
       int nc = 0;
@@ -265,6 +300,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
           }
         }
       }
+      if (warp == MMA_WARP + 1) VQ_ADD(8, t_e2);
+      VQ_T(t_e3);
       // accumulator drained: hand it back to the MMA warp before the (rare, slow) exact re-scoring
       tc_fence_before();
       __syncwarp();
@@ -272,6 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
 
       // ---- exact fp32 re-scoring of rows with more than one candidate: whole warp per row, 8 lanes per code ----
       unsigned need = __ballot_sync(0xffffffffu, nc > 0 && g < rows);
+      if (warp == MMA_WARP + 1) { VQ_CNT(12, __popc(need)); VQ_CNT(13, __popc(__ballot_sync(0xffffffffu, nc > MAXC))); }
       const int grp = lane >> 3, gl = lane & 7;
       while (need) {
         const int src = __ffs(need) - 1;
@@ -322,12 +360,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         if (lane == src && bk < NC) k1 = bk;      // all-NaN rows keep the screen's answer (0, like torch.argmin)
       }
       if (g < rows) index[g] = (long long)k1;
+      if (warp == MMA_WARP + 1) VQ_ADD(9, t_e3);
     }
   }
 
   // teardown
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) VQ_ADD(10, t_kernel);
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
@@ -359,3 +399,19 @@ extern "C" int pm_l2_argmin_tc(const float* z, long long rows, const float* code
   l2_argmin_tc_kernel<<<(unsigned)grid, NTHREADS, kSmem, (cudaStream_t)stream>>>(z, rows, codebook, e2, index);
   PM_LAUNCH_CHECK();
 }
+
+#ifdef PM_VQ_TIMING
+extern "C" int pm_vq_timing_reset() {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  void* d = nullptr;
+  e = cudaGetSymbolAddress(&d, pm_vq_stamps);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(d, 0, sizeof(unsigned long long) * 16);
+}
+extern "C" int pm_vq_timing_read(unsigned long long* host) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(host, pm_vq_stamps, sizeof(unsigned long long) * 16);
+}
+#endif
