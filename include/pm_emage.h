@@ -98,6 +98,17 @@ int pm_attention_f32(const float* Q, int ldq, const float* K, int ldk, const flo
                      float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim,
                      uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
+/* Same op on the tcgen05 tensor cores for the fp16x3 engine: Q, K, V are two-plane fp16 activations (x = (p0+p1)/64,
+ * plane stride *_ps, clip stride *_bs, row stride ld* elements, *_cols valid columns; head h of Q starts at column
+ * q_col0 + h*hd, likewise K and V - so the packed q|k|v projection output is consumed in place through TMA).
+ * S = Q K^T and O = P V run as 3-product fp16 UMMAs (M=64) with S and O in TMEM, softmax in fp32 registers.
+ * Output: fp32 O (nullable) and / or two fp16 planes (p_nsplit = 2 | PM_FMT_F16). */
+int pm_attention_tc(const uint16_t* Q, long long q_ps, long long q_bs, int ldq, int q_cols, int q_col0,
+                    const uint16_t* K, long long k_ps, long long k_bs, int ldk, int k_cols, int k_col0,
+                    const uint16_t* V, long long v_ps, long long v_bs, int ldv, int v_cols, int v_col0,
+                    float* O, int ldo, int batch, int heads, int tq, int tk, int head_dim,
+                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
+
 /* ---- broadcast adds: out[b,t,:] = ((x[b,t,:] + first) + second), each of first/second chosen by code:
  * 0 = nothing, 1 = pe[t,:] (PeriodicPositionalEncoding P.py:341-343), 2 = spk[b,:] (speaker embedding
  * row repeated over t, M.py:285-286).  x nullable (treated as 0).  Preserves the reference's add order

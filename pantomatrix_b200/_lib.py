@@ -27,6 +27,8 @@ SIGNATURES = {
     "pm_wav_stem_f32": [_p, _ll, _ll, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p],
     "pm_add_layernorm_f32": [_p, _p, _p, _p, _p, _ll, _i, _f, _p, _ll, _i, _i, _p],
     "pm_attention_f32": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _i, _i, _p],
+    "pm_attention_tc": [_p, _ll, _ll, _i, _i, _i, _p, _ll, _ll, _i, _i, _i, _p, _ll, _ll, _i, _i, _i,
+                        _p, _i, _i, _i, _i, _i, _i, _p, _ll, _i, _i, _p],
     "pm_add_rows_f32": [_p, _p, _p, _i, _i, _p, _i, _i, _i, _p, _ll, _i, _i, _p],
     "pm_add2_f32": [_p, _p, _p, _ll, _i, _p, _ll, _i, _i, _p],
     "pm_window_input_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _i, _i, _p],

@@ -118,3 +118,33 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
 // UMMA shared-memory descriptor, K-major operand in the canonical 128-byte-swizzle layout (8-row groups 1024 B
 // apart, version 1 = sm_100): OR in (smem byte address >> 4) & 0x3FFF.
 constexpr uint64_t UMMA_DESC_K_SW128 = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+
+// ---- host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency) ----
+// 2-byte elements (bf16 / fp16), 128-byte swizzle, zero fill out of bounds.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static inline bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box, bool f16 = false) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  return fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+            const_cast<void*>(base), dims, strides_bytes, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+

@@ -309,7 +309,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
 
       // ---- exact fp32 re-scoring of rows with more than one candidate: whole warp per row, 8 lanes per code ----
       unsigned need = __ballot_sync(0xffffffffu, nc > 0 && g < rows);
-      if (warp == MMA_WARP + 1) { VQ_CNT(12, __popc(need)); VQ_CNT(13, __popc(__ballot_sync(0xffffffffu, nc > MAXC))); }
+#ifdef PM_VQ_TIMING
+      {
+        const unsigned over = __ballot_sync(0xffffffffu, nc > MAXC);
+        if (warp == MMA_WARP + 1) { VQ_CNT(12, __popc(need)); VQ_CNT(13, __popc(over)); }
+      }
+#endif
       const int grp = lane >> 3, gl = lane & 7;
       while (need) {
         const int src = __ffs(need) - 1;

@@ -336,8 +336,9 @@ class _Layer:
         self.norms = [(sd[f"{p}.norm{i + 1}.weight"].contiguous(), sd[f"{p}.norm{i + 1}.bias"].contiguous()) for i in range(n)]
 
     def project_memory(self, mem):
-        """K|V projection of a cross-attention memory (bs, tk, E) -> (bs, tk, 2E) fp32."""
-        return self.ca.kv(mem)
+        """K|V projection of a cross-attention memory (bs, tk, E) -> (bs, tk, 2E): fp32, or the fp16 operand planes
+        the tensor-core attention kernel reads in place."""
+        return self.ca.kv(mem, want="p" if _attn_tc() else "f")
 
     def __call__(self, x, mem_kv=None, want="f"):
         """x: fp32 tensor or Act(f, p) of (bs, t, E).  Returns the layer output in the requested form."""
@@ -345,22 +346,44 @@ class _Layer:
         xf = _f32(x)
         bs, t, E = xf.shape
         hd = E // NHEAD
-        qkv = self.sa.qkv(x).view(bs * t, 3 * E)
-        att = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], bs, NHEAD, t, t, hd, nsplit=ns, f32=ns == 0)
+        tc = _attn_tc()
+        if tc:                                  # packed q|k|v planes straight from the GEMM epilogue, read in place by TMA
+            qkv = self.sa.qkv(x, want="p").p
+            att = ops.attention_tc(qkv, 0, qkv, E, qkv, 2 * E, bs, NHEAD, t, t, hd, nsplit=ns)
+        else:
+            qkv = self.sa.qkv(x).view(bs * t, 3 * E)
+            att = ops.attention(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], bs, NHEAD, t, t, hd, nsplit=ns, f32=ns == 0)
         x = ops.add_layernorm(self.sa.out(_view3(att, bs, t, E), residual=xf), None, *self.norms[0], nsplit=ns)
         k = 1
         if self.ca is not None:
-            tk = mem_kv.shape[1]
-            assert mem_kv.is_contiguous()
-            kv = mem_kv.view(bs * tk, 2 * E)
-            q = self.ca.q(x).view(bs * t, E)
-            att = ops.attention(q, kv[:, :E], kv[:, E:], bs, NHEAD, t, tk, hd, nsplit=ns, f32=ns == 0)
+            if tc:
+                kv = mem_kv.p if isinstance(mem_kv, ops.Act) else mem_kv
+                att = ops.attention_tc(self.ca.q(x, want="p").p, 0, kv, 0, kv, E, bs, NHEAD, t, kv.rows, hd, nsplit=ns)
+            else:
+                tk = mem_kv.shape[1]
+                assert mem_kv.is_contiguous()
+                kv = mem_kv.view(bs * tk, 2 * E)
+                q = self.ca.q(x).view(bs * t, E)
+                att = ops.attention(q, kv[:, :E], kv[:, E:], bs, NHEAD, t, tk, hd, nsplit=ns, f32=ns == 0)
             x = ops.add_layernorm(self.ca.out(_view3(att, bs, t, E), residual=_f32(x)), None, *self.norms[1], nsplit=ns)
             k = 2
         h = self.l1(x, act=ops.ACT_RELU, want="p")
         want_ns = ns if "p" in want else 0
         y = ops.add_layernorm(self.l2(h, residual=_f32(x)), None, *self.norms[k], nsplit=want_ns, f32="f" in want or want_ns == 0)
         return y
+
+
+def _attn_tc():
+    """The tcgen05 attention kernel consumes two-plane fp16 operands: the fp16x3 engine."""
+    return _STATE["nsplit"] == 2 and ops.plane_format() == "fp16"
+
+
+def _window_of(x, j, bs):
+    """Window j (clips j*bs .. (j+1)*bs) of a window-major hoisted tensor: fp32 tensor or plane Act."""
+    if isinstance(x, ops.Act):
+        pl = x.p
+        return ops.Act(None, ops.Planes(pl.t[:, j * bs:(j + 1) * bs], pl.rows, pl.ch, 0))
+    return x[j * bs:(j + 1) * bs]
 
 
 def _view3(att, bs, t, E):
@@ -590,9 +613,8 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
         mem_face, kv = engine.audio_phase(audio, s0 * spf, (window - pre) * spf, count, t * spf, t)
         E = engine.E
         mem_face = mem_face.view(count, bs, t, E)                 # window-major: each window is contiguous
-        kv = [k.view(count, bs, k.shape[1], 2 * E) for k in kv]
         for j in range(count):
-            hoisted[first + j] = (mem_face[j], [k[j] for k in kv])
+            hoisted[first + j] = (mem_face[j], [_window_of(k, j, bs) for k in kv])
 
     out_len = sum(k for _, _, k in plan)
     acc = {k + p: torch.empty(bs, out_len, 256, device=dev) for k in ("rec_", "cls_") for p in PARTS}

@@ -178,6 +178,24 @@ def attention(q, k, v, batch, heads, tq, tk, head_dim, nsplit=0, f32=True):
     return _result(out, pl, nsplit)
 
 
+def attention_tc(q, q_col0, k, k_col0, v, v_col0, batch, heads, tq, tk, head_dim, nsplit=2, f32=False):
+    """Attention on the tcgen05 tensor cores (fp16x3 engine).  q / k / v: two-plane fp16 Planes whose columns
+    [*_col0 + h*head_dim, ...) hold head h (the packed q|k|v or k|v projection output is passed as is)."""
+    for pl, rows in ((q, tq), (k, tk), (v, tk)):
+        assert pl.t.dtype == torch.float16 and pl.t.shape[0] == 2 and pl.t.shape[1] == batch and pl.rows == rows, \
+            "attention_tc needs two-plane fp16 operands of (batch, rows, ch)"
+    E = heads * head_dim
+    dev = q.t.device
+    out = torch.empty(batch * tq, E, device=dev, dtype=torch.float32) if (f32 or not nsplit) else None
+    pl = _new_planes(nsplit, (batch, tq), E, dev, dtype=torch.float16) if nsplit else None
+    _call("pm_attention_tc",
+          q.t.data_ptr(), q.t.stride(0), q.t.stride(1), q.t.stride(2), q.ch, q_col0,
+          k.t.data_ptr(), k.t.stride(0), k.t.stride(1), k.t.stride(2), k.ch, k_col0,
+          v.t.data_ptr(), v.t.stride(0), v.t.stride(1), v.t.stride(2), v.ch, v_col0,
+          _ptr(out), E, batch, heads, tq, tk, head_dim, *_pargs(pl), _stream())
+    return _result(out, pl, nsplit)
+
+
 def add_rows(x, pe, spk, first, second, batch, rows, ch, nsplit=0, f32=True):
     dev = (pe if pe is not None else spk).device
     out = torch.empty(batch, rows, ch, device=dev, dtype=torch.float32) if (f32 or not nsplit) else None

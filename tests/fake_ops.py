@@ -88,6 +88,12 @@ def attention(q, k, v, batch, heads, tq, tk, head_dim, nsplit=0, f32=True):
     return _res((att @ vv).transpose(1, 2).reshape(batch * tq, E), nsplit, f32, lead=(batch, tq))
 
 
+def attention_tc(q, q_col0, k, k_col0, v, v_col0, batch, heads, tq, tk, head_dim, nsplit=2, f32=False):
+    E = heads * head_dim
+    val = lambda pl, c0, rows: (pl.t[:, :, :rows, c0:c0 + E].float().sum(0) / _real.F16_ACT_SCALE).reshape(batch * rows, E)
+    return attention(val(q, q_col0, tq), val(k, k_col0, tk), val(v, v_col0, tk), batch, heads, tq, tk, head_dim, nsplit=nsplit, f32=f32)
+
+
 def add_rows(x, pe, spk, first, second, batch, rows, ch, nsplit=0, f32=True):
     v = torch.zeros(batch, rows, ch) if x is None else x.reshape(batch, rows, ch)
     for code in (first, second):

@@ -122,6 +122,32 @@ def test_attention(ops, bs, tq, tk):
     _close(got, want, 1e-5, 1e-5)
 
 
+@pytest.mark.parametrize("bs,tq,tk", [(5, 64, 64), (3, 60, 60), (2, 11, 12), (2, 64, 60), (2, 1, 1), (32, 64, 64)])
+def test_attention_tc(ops, bs, tq, tk):
+    """tcgen05 attention of the fp16x3 engine: two-plane fp16 operands read in place from the packed q|k|v (self) or
+    q + k|v (cross) projection outputs; fp32 and plane outputs against float64."""
+    E, H, hd = 768, 4, 192
+    qkv = _rand(bs, tq, 3 * E, seed=20)
+    kv = _rand(bs, tk, 2 * E, seed=21)
+    ops.set_plane_format("fp16")
+    try:
+        qp, kvp = ops.split_bf16(qkv, 2), ops.split_bf16(kv, 2)
+        cross = ops.attention_tc(qp, 0, kvp, 0, kvp, E, bs, H, tq, tk, hd, nsplit=2, f32=True)
+        if tq == tk:
+            self_att = ops.attention_tc(qp, 0, qp, E, qp, 2 * E, bs, H, tq, tq, hd, nsplit=0)
+    finally:
+        ops.set_plane_format("bf16")
+
+    def ref(q, k, v):
+        q, k, v = (x.double().reshape(bs, -1, H, hd).transpose(1, 2) for x in (q, k, v))
+        return (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v).transpose(1, 2).reshape(bs * tq, E)
+    want = ref(qkv[..., :E], kv[..., :E], kv[..., E:])
+    _close(cross.f, want, 1e-5, 1e-5)
+    assert (_planes_value(cross.p).reshape(bs * tq, E) - cross.f).abs().max() <= 2.0 ** -21 * cross.f.abs().max()
+    if tq == tk:
+        _close(self_att, ref(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:]), 1e-5, 1e-5)
+
+
 def test_broadcast_adds_are_exact(ops):
     bs, t, ch = 3, 60, 768
     x, pe, spk = _rand(bs, t, ch, seed=22), _rand(128, ch, seed=23), _rand(bs, ch, seed=24)
