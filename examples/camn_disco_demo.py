@@ -38,7 +38,7 @@ def main():
     device = torch.device("cuda")
     if args.synthetic:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import build_lstm_product
+        from synthetic_models import build_lstm_product
         model = build_lstm_product(args.model, device=device)
     else:
         cls = CamnAudioModel if args.model == "camn" else DiscoAudioModel

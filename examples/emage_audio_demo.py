@@ -26,7 +26,7 @@ from pantomatrix_b200.pipeline import generate  # noqa: E402
 def load_models(args, device):
     if args.synthetic:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import build_product
+        from synthetic_models import build_product
         return build_product(seed=0, device=device)
     ck = args.checkpoint
     vq = {p: EmageVQVAEConv.from_pretrained(ck, subfolder=f"emage_vq/{p}").to(device) for p in ("face", "upper", "lower", "hands")}

@@ -28,9 +28,11 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 3
+#define PM_ABI_VERSION 4
 #define PM_FMT_F16 0x100
 int pm_abi_version(void);
+/* cudaMemsetAsync on `stream` (a memset node under graph capture, not a kernel): zeroed slack rows, flags */
+int pm_memset_async(void* ptr, int value, long long bytes, void* stream);
 /* compute capability major*10+minor of the current device, or <0 */
 int pm_device_cc(void);
 
@@ -121,11 +123,13 @@ int pm_add2_f32(const float* a, const float* b, float* out, long long n, int ch,
                 uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- window assembly (M.py:384-391 and 267-268 fused): builds one window's motion-encoder input.
- * motion/mask: (batch, total_len, ch) full-sequence tensors; seed: (batch, pre, ch) decoded last frames.
- * For frame f<pre: v = mask==0 ? motion : seed, window mask forced 0; else v = motion, m = mask.
+ * motion/mask: (batch, total_len, ch) full-sequence tensors, either may be NULL = inference()'s defaults (identity
+ * rot6d + zero trans/contact; all masked, M.py:369-377); seed: (batch, pre, ch) decoded last frames, clip stride seed_bs.
+ * For frame f<pre: v = mask==0 ? motion : seed (seed NULL = the first window, whose seed is motion[:, :pre] itself,
+ * M.py:379), window mask forced 0; else v = motion, m = mask.
  * out = (m == 1) ? mask_embedding[c] : v. */
 int pm_window_input_f32(const float* motion, const float* mask, const float* seed, const float* mask_embedding,
-                        float* out, int batch, int total_len, int start, int win_len, int pre, int ch,
+                        float* out, int batch, int total_len, int start, int win_len, int pre, int ch, long long seed_bs,
                         uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- VQ ------------------------------------------------------------------------------------------ */
@@ -138,14 +142,19 @@ int pm_window_input_f32(const float* motion, const float* mask, const float* see
  *                        max_ctas > 0 caps the persistent grid (<= 0: one CTA per SM).
  *   pm_l2_argmin_simt_f32  n_codes a multiple of 64: register-tiled fp32 SIMT kernel (sequential-k fp32 FMA).
  *   pm_l2_argmin_f32     dispatcher the product calls: tc for 256-code codebooks, simt otherwise. */
-int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
-                     int n_codes, int e_dim, long long* index, void* stream);
-int pm_l2_argmin_tc(const float* z, long long rows, const float* codebook, const float* e2,
-                    int n_codes, int e_dim, long long* index, int max_ctas, void* stream);
-int pm_l2_argmin_simt_f32(const float* z, long long rows, const float* codebook, const float* e2,
-                          int n_codes, int e_dim, long long* index, void* stream);
-/* index = first argmax over the last dim: torch.max(F.log_softmax(x,2),2)[1], M.py:398-401 (monotone). */
-int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream);
+int pm_l2_argmin_f32(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                     const float* codebook, const float* e2, int n_codes, int e_dim, long long* index, void* stream);
+int pm_l2_argmin_tc(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                    const float* codebook, const float* e2, int n_codes, int e_dim, long long* index, int max_ctas,
+                    void* stream);
+int pm_l2_argmin_simt_f32(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                          const float* codebook, const float* e2, int n_codes, int e_dim, long long* index, void* stream);
+/* index = first argmax over the last dim: torch.max(F.log_softmax(x,2),2)[1], M.py:398-401 (monotone).
+ * Row r of the (batch, rows_per_batch, ch) view lives at x + (r / rows_per_batch)*x_bs + (r % rows_per_batch)*ldx
+ * (rows_per_batch <= 0: one dense matrix; the same convention addresses z in pm_l2_argmin_* with ld = 256), so the
+ * tail frames of a window are read in place.  nonfinite (nullable): set to 1 when any element read is NaN / inf. */
+int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, int rows_per_batch, long long x_bs,
+                      long long* index, int* nonfinite, void* stream);
 /* out[r,:] = codebook[index[r],:]: Quantizer.get_codebook_entry P.py:166-170, nn.Embedding M.py:285-286.
  * n_table = rows of `codebook`; indices outside [0, n_table) are clamped (never an out-of-bounds read). */
 int pm_gather_rows_f32(const float* codebook, long long n_table, const long long* index, long long rows, int ch,
@@ -162,7 +171,7 @@ int pm_pose_compose_f32(const float* face, const float* upper, const float* hand
 /* ---- global translation: velocity2position P.py:107-115 as used by get_global_motion M.py:195-205 --
  * rec (batch, t, ld) global-AE output; vel = rec[..., 54:57]; x/z integrated sequentially with dt,
  * y copied; ref_trans (batch,3) start position. */
-int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, float dt,
+int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, int ref_bs, float dt,
                         float* trans, int batch, int t, void* stream);
 
 /* ---- CaMN / DisCo (BASELINE configs[2],[3]) ------------------------------------------------------- */

@@ -151,7 +151,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256) window_input_kernel(
     const float* __restrict__ motion, const float* __restrict__ mask, const float* __restrict__ seed,
     const float* __restrict__ mask_embedding, float* __restrict__ out,
-    int batch, int total_len, int start, int win_len, int pre, int ch, PmPlanes P) {
+    int batch, int total_len, int start, int win_len, int pre, int ch, long long seed_bs, PmPlanes P) {
   const long long total = (long long)batch * win_len * ch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -159,10 +159,12 @@ __global__ void __launch_bounds__(256) window_input_kernel(
     const long long bf = i / ch;
     const int f = (int)(bf % win_len), b = (int)(bf / win_len);
     const long long src = ((long long)b * total_len + start + f) * ch + c;
-    float m = mask[src];
-    float v = motion[src];
+    // defaults of inference() when the caller passes no masked_motion / mask (M.py:369-377): identity rotations in
+    // rot6d ([1,0,0,0,1,0] per joint) + zero trans / contact, everything masked
+    float m = mask ? mask[src] : 1.f;
+    float v = motion ? motion[src] : ((c < ch - 7 && (c % 6 == 0 || c % 6 == 4)) ? 1.f : 0.f);
     if (f < pre) {                    // M.py:386-391
-      if (m != 0.f) v = seed[((long long)b * pre + f) * ch + c];
+      if (m != 0.f && seed) v = seed[(long long)b * seed_bs + (long long)f * ch + c];   // no seed yet (first window): motion itself, M.py:379
       m = 0.f;
     }
     const float o = (m == 1.f) ? mask_embedding[c] : v;   // M.py:267-268
@@ -263,9 +265,9 @@ extern "C" int pm_add2_f32(const float* a, const float* b, float* out, long long
 
 extern "C" int pm_window_input_f32(const float* motion, const float* mask, const float* seed,
                                    const float* mask_embedding, float* out, int batch, int total_len,
-                                   int start, int win_len, int pre, int ch,
+                                   int start, int win_len, int pre, int ch, long long seed_bs,
                                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
-  PM_REQUIRE(motion && mask && mask_embedding && (out || planes) && (seed || pre == 0));
+  PM_REQUIRE(mask_embedding && (out || planes));
   PM_TAKE_FMT(p_nsplit, f16);
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, ch, false));
   const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, p_nsplit};
@@ -273,8 +275,8 @@ extern "C" int pm_window_input_f32(const float* motion, const float* mask, const
   const long long total = (long long)batch * win_len * ch;
   if (total == 0) return PM_OK;
   if (f16) window_input_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, P);
+      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, seed_bs, P);
   else window_input_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, P);
+      motion, mask, seed, mask_embedding, out, batch, total_len, start, win_len, pre, ch, seed_bs, P);
   PM_LAUNCH_CHECK();
 }

@@ -104,14 +104,14 @@ __global__ void __launch_bounds__(256) pose_compose_kernel(
 }
 
 __global__ void __launch_bounds__(64) global_trans_kernel(const float* __restrict__ rec, int ld, int vel_off,
-                                                          const float* __restrict__ ref_trans, float dt,
+                                                          const float* __restrict__ ref_trans, int ref_bs, float dt,
                                                           float* __restrict__ trans, int t) {
   const int b = blockIdx.x;
   const float* __restrict__ v = rec + (long long)b * t * ld + vel_off;
   float* __restrict__ o = trans + (long long)b * t * 3;
   if (threadIdx.x < 2) {                          // x (axis 0) and z (axis 2): sequential, reference order
     const int ax = threadIdx.x * 2;
-    float pos = ref_trans[b * 3 + ax];
+    float pos = ref_trans[(long long)b * ref_bs + ax];
     o[ax] = pos;
     for (int i = 1; i < t; ++i) {
       pos = v[(long long)(i - 1) * ld + ax] * dt + pos;     // one rounding per op (-fmad=false)
@@ -193,10 +193,10 @@ extern "C" int pm_pose_compose_f32(const float* face, const float* upper, const 
   PM_LAUNCH_CHECK();
 }
 
-extern "C" int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, float dt,
+extern "C" int pm_global_trans_f32(const float* rec, int ld, int vel_off, const float* ref_trans, int ref_bs, float dt,
                                    float* trans, int batch, int t, void* stream) {
-  PM_REQUIRE(rec && ref_trans && trans && batch >= 0 && t >= 0 && ld >= vel_off + 3);
+  PM_REQUIRE(rec && ref_trans && trans && batch >= 0 && t >= 0 && ld >= vel_off + 3 && ref_bs >= 0);
   if (batch == 0 || t == 0) return PM_OK;
-  global_trans_kernel<<<batch, 64, 0, (cudaStream_t)stream>>>(rec, ld, vel_off, ref_trans, dt, trans, t);
+  global_trans_kernel<<<batch, 64, 0, (cudaStream_t)stream>>>(rec, ld, vel_off, ref_trans, ref_bs, dt, trans, t);
   PM_LAUNCH_CHECK();
 }

@@ -15,7 +15,7 @@ constexpr int NT = 256;
 // lowest index winning ties (torch.argmin).  The dot products are the hot part: a 64x64x256 register-
 // tiled product per chunk, z tile resident in smem, codebook (256 KB) streamed from L2 in 64 KB chunks.
 __global__ void __launch_bounds__(NT) l2_argmin_kernel(
-    const float* __restrict__ z, long long rows, const float* __restrict__ codebook,
+    const float* __restrict__ z, long long rows, int rows_per_batch, long long z_bs, const float* __restrict__ codebook,
     const float* __restrict__ e2, int n_codes, long long* __restrict__ index) {
   extern __shared__ float smem[];
   float* Zs = smem;                 // [RT][EDP]
@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(NT) l2_argmin_kernel(
   for (int i = tid; i < RT * (ED / 4); i += NT) {          // coalesced float4 loads of the z tile
     const int r = i / (ED / 4), c4 = i % (ED / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < rows) v = *reinterpret_cast<const float4*>(z + (r0 + r) * ED + c4 * 4);
+    if (r0 + r < rows)
+      v = *reinterpret_cast<const float4*>(z + ((r0 + r) / rows_per_batch) * z_bs + ((r0 + r) % rows_per_batch) * ED + c4 * 4);
     float* d = Zs + r * EDP + c4 * 4;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
@@ -104,17 +105,21 @@ __global__ void __launch_bounds__(NT) l2_argmin_kernel(
 constexpr size_t kL2Smem = (size_t)(RT * EDP + CT * EDP + RT) * sizeof(float);
 
 __global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict__ x, long long rows, int ch,
-                                                         int ldx, long long* __restrict__ index) {
+                                                         int ldx, int rows_per_batch, long long x_bs,
+                                                         long long* __restrict__ index, int* __restrict__ nonfinite) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* __restrict__ xr = x + row * ldx;
+  const float* __restrict__ xr = x + (row / rows_per_batch) * x_bs + (row % rows_per_batch) * ldx;
   float best = -INFINITY;
   int bk = 0x7fffffff;
+  bool bad = false;
   for (int c = lane; c < ch; c += 32) {        // increasing c per lane: strict > keeps the first max
     const float v = xr[c];
+    bad |= !isfinite(v);
     if (v > best || bk == 0x7fffffff) { best = v; bk = c; }
   }
+  if (nonfinite && __any_sync(0xffffffffu, bad) && lane == 0) atomicExch(nonfinite, 1);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -154,9 +159,12 @@ __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict
 
 }  // namespace
 
-extern "C" int pm_l2_argmin_simt_f32(const float* z, long long rows, const float* codebook, const float* e2,
+extern "C" int pm_l2_argmin_simt_f32(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                                     const float* codebook, const float* e2,
                                      int n_codes, int e_dim, long long* index, void* stream) {
   PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
+  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; z_bs = 0; }
+  PM_REQUIRE((z_bs & 3) == 0);
   if (e_dim != ED || n_codes <= 0 || n_codes % CT != 0) return PM_EUNSUPPORTED;
   if (rows == 0) return PM_OK;
   {   // per device, cheap: no process-wide "configured" flag (a second GPU in the same process needs it too)
@@ -165,24 +173,28 @@ extern "C" int pm_l2_argmin_simt_f32(const float* z, long long rows, const float
   }
   const long long grid = (rows + RT - 1) / RT;
   PM_REQUIRE(grid <= 0x7fffffffLL);
-  l2_argmin_kernel<<<(unsigned)grid, NT, kL2Smem, (cudaStream_t)stream>>>(z, rows, codebook, e2, n_codes, index);
+  l2_argmin_kernel<<<(unsigned)grid, NT, kL2Smem, (cudaStream_t)stream>>>(z, rows, rows_per_batch, z_bs, codebook, e2, n_codes, index);
   PM_LAUNCH_CHECK();
 }
 
-extern "C" int pm_l2_argmin_f32(const float* z, long long rows, const float* codebook, const float* e2,
+extern "C" int pm_l2_argmin_f32(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                                const float* codebook, const float* e2,
                                 int n_codes, int e_dim, long long* index, void* stream) {
   // 256 codes x 256 dims (every EMAGE codebook): tensor-core screen + exact fp32 re-scoring (pm_vq_tc.cu);
   // other codebook sizes: the fp32 SIMT kernel above.  Both return the fp32 argmin with first-index ties.
   if (n_codes == 256 && e_dim == 256 && z && codebook && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(codebook) & 15) == 0)
-    return pm_l2_argmin_tc(z, rows, codebook, e2, n_codes, e_dim, index, 0, stream);
-  return pm_l2_argmin_simt_f32(z, rows, codebook, e2, n_codes, e_dim, index, stream);
+    return pm_l2_argmin_tc(z, rows, rows_per_batch, z_bs, codebook, e2, n_codes, e_dim, index, 0, stream);
+  return pm_l2_argmin_simt_f32(z, rows, rows_per_batch, z_bs, codebook, e2, n_codes, e_dim, index, stream);
 }
 
-extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, long long* index, void* stream) {
+extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx, int rows_per_batch, long long x_bs,
+                                 long long* index, int* nonfinite, void* stream) {
   PM_REQUIRE(x && index && rows >= 0 && ch > 0 && ldx >= ch);
   if (rows == 0) return PM_OK;
-  row_argmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, ch, ldx, index);
+  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; x_bs = 0; }      // one dense (rows, ldx) matrix
+  row_argmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, ch, ldx, rows_per_batch, x_bs,
+                                                                                  index, nonfinite);
   PM_LAUNCH_CHECK();
 }
 

@@ -78,6 +78,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ void prefetch_row(const float* p) {           // one 1 KB row = 8 cache lines
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32 * i));
+}
 // exact power of two 2^s as a float, s in [-126, 127]
 __device__ __forceinline__ float pow2i(int s) { return __uint_as_float((uint32_t)(s + 127) << 23); }
 // s such that m * 2^s lies in [2^13, 2^14) for a finite normal m > 0; 0 for zero / subnormal / non-finite m
@@ -89,8 +93,10 @@ __device__ __forceinline__ int scale_exp(float m) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
-    const float* __restrict__ z, long long rows, const float* __restrict__ codebook, const float* __restrict__ e2,
-    long long* __restrict__ index) {
+    const float* __restrict__ z, long long rows, int rows_per_batch, long long z_bs, const float* __restrict__ codebook,
+    const float* __restrict__ e2, long long* __restrict__ index) {
+  // row g of the (batch, rows_per_batch, 256) view: z + (g / rows_per_batch) * z_bs + (g % rows_per_batch) * 256
+  auto row_ptr = [&](long long g) { return z + (g / rows_per_batch) * z_bs + (g % rows_per_batch) * ED; };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sm_u = smem_u32(sm);
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         for (int j = 0; j < 8; ++j) {
           const long long g = r0 + rb + j;
           if (g < rows) {
-            const float4* p = reinterpret_cast<const float4*>(z + g * ED);
+            const float4* p = reinterpret_cast<const float4*>(row_ptr(g));
             v[j][0] = ldg_stream4(p + lane);
             v[j][1] = ldg_stream4(p + 32 + lane);
           } else {
@@ -257,48 +263,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       if (warp == MMA_WARP + 1) VQ_ADD(6, t_e0);
       VQ_T(t_e1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * NC;
-      // pass 1: minimum of the screened distances (first index wins)
-      float m1 = INFINITY;
-      int k1 = 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c0, acc);
+      // pass 1: minimum of the screened distances (first index wins).  Four independent running minima (the chain
+      // of 256 dependent compare-selects was latency bound) and the next TMEM chunk in flight while this one is reduced.
+      float mm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+      int kk[4] = {0, 1, 2, 3};
+      uint32_t accA[32], accB[32];
+      auto reduce_chunk = [&](const uint32_t (&acc)[32], int c0) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
           const float d0 = fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), d1 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y);
           const float d2 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), d3 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w);
-          if (d0 < m1) { m1 = d0; k1 = c0 + 4 * j4; }
-          if (d1 < m1) { m1 = d1; k1 = c0 + 4 * j4 + 1; }
-          if (d2 < m1) { m1 = d2; k1 = c0 + 4 * j4 + 2; }
-          if (d3 < m1) { m1 = d3; k1 = c0 + 4 * j4 + 3; }
+          if (d0 < mm[0]) { mm[0] = d0; kk[0] = c0 + 4 * j4; }
+          if (d1 < mm[1]) { mm[1] = d1; kk[1] = c0 + 4 * j4 + 1; }
+          if (d2 < mm[2]) { mm[2] = d2; kk[2] = c0 + 4 * j4 + 2; }
+          if (d3 < mm[3]) { mm[3] = d3; kk[3] = c0 + 4 * j4 + 3; }
         }
+      };
+      tmem_ld32_issue(taddr, accA);
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC; c0 += 64) {
+        tmem_ld32_wait(accA);
+        tmem_ld32_issue(taddr + c0 + 32, accB);
+        reduce_chunk(accA, c0);
+        tmem_ld32_wait(accB);
+        tmem_ld32_issue(taddr + ((c0 + 64) & (NC - 1)), accA);       // wraps to chunk 0: the first chunk of pass 2
+        reduce_chunk(accB, c0 + 32);
       }
+      float m1 = mm[0];
+      int k1 = kk[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (mm[u] < m1 || (mm[u] == m1 && kk[u] < k1)) { m1 = mm[u]; k1 = kk[u]; }
       if (warp == MMA_WARP + 1) VQ_ADD(7, t_e1);
       VQ_T(t_e2);
       // pass 2: every other code within tau of the minimum
       const float thr = m1 + inf.y;
       int nc = 0;
       uint8_t* my = cands + trow * MAXC;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c0, acc);
+      auto collect_chunk = [&](const uint32_t (&acc)[32], int c0) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
           const float d[4] = {fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y),
                               fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w)};
+          if (d[0] <= thr || d[1] <= thr || d[2] <= thr || d[3] <= thr) {       // rare: one branch per four codes
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k = c0 + 4 * j4 + u;
-            if (d[u] <= thr && k != k1) {
-              if (nc < MAXC) my[nc] = (uint8_t)k;
-              ++nc;
+            for (int u = 0; u < 4; ++u) {
+              const int k = c0 + 4 * j4 + u;
+              if (d[u] <= thr && k != k1) {
+                if (nc < MAXC) {
+                  my[nc] = (uint8_t)k;
+                  // this row will be re-scored after the pass: pull its operands into L1 now (the re-scoring loop
+                  // was a chain of L2 round trips, ~2300 cycles per row; profiles/vq_timeline_r2.md)
+                  if (nc == 0 && g < rows) { prefetch_row(row_ptr(g)); prefetch_row(codebook + (long long)k1 * ED); }
+                  prefetch_row(codebook + (long long)k * ED);
+                }
+                ++nc;
+              }
             }
           }
         }
+      };
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC; c0 += 64) {
+        tmem_ld32_wait(accA);
+        tmem_ld32_issue(taddr + c0 + 32, accB);
+        collect_chunk(accA, c0);
+        tmem_ld32_wait(accB);
+        if (c0 + 64 < NC) tmem_ld32_issue(taddr + c0 + 64, accA);
+        collect_chunk(accB, c0 + 32);
       }
       if (warp == MMA_WARP + 1) VQ_ADD(8, t_e2);
       VQ_T(t_e3);
@@ -324,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         const bool all = nsrc > MAXC;                                    // list overflowed: every code is a candidate
         const int ncand = all ? NC : nsrc + 1;
         const long long gr = tile * TM + q * 32 + src;
-        const float4* zr = reinterpret_cast<const float4*>(z + gr * ED);
+        const float4* zr = reinterpret_cast<const float4*>(row_ptr(gr));
         float4 zv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) zv[i] = __ldg(zr + gl + 8 * i);
@@ -383,9 +417,12 @@ constexpr size_t kSmem = Smem::TOTAL + 1024;
 
 }  // namespace
 
-extern "C" int pm_l2_argmin_tc(const float* z, long long rows, const float* codebook, const float* e2,
+extern "C" int pm_l2_argmin_tc(const float* z, long long rows, int rows_per_batch, long long z_bs,
+                               const float* codebook, const float* e2,
                                int n_codes, int e_dim, long long* index, int max_ctas, void* stream) {
   PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
+  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; z_bs = 0; }      // one dense (rows, 256) matrix
+  PM_REQUIRE((z_bs & 3) == 0);
   if (e_dim != ED || n_codes != NC) return PM_EUNSUPPORTED;
   PM_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
   if (rows == 0) return PM_OK;
@@ -401,7 +438,7 @@ extern "C" int pm_l2_argmin_tc(const float* z, long long rows, const float* code
   const long long tiles = (rows + TM - 1) / TM;
   long long grid = tiles < sms ? tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  l2_argmin_tc_kernel<<<(unsigned)grid, NTHREADS, kSmem, (cudaStream_t)stream>>>(z, rows, codebook, e2, index);
+  l2_argmin_tc_kernel<<<(unsigned)grid, NTHREADS, kSmem, (cudaStream_t)stream>>>(z, rows, rows_per_batch, z_bs, codebook, e2, index);
   PM_LAUNCH_CHECK();
 }
 

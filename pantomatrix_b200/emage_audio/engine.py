@@ -12,7 +12,9 @@ Schedule differences from the reference that do not change results beyond fp32 r
     layers.  Each window still sees its own zero-padded audio slice, as in the
     reference (M.py:393-396), so window-local conv results are reproduced exactly.
   * In-loop VQ decodes only produce the seed frames (M.py:418): the conv decoders are run on the last
-    `SEED_DECODE_FRAMES` frames, which covers their receptive field (+-9 frames for vae_layer=4).
+    seed_frames + (5 + vae_layer) frames of the window, which covers their receptive field (seed_decode_frames()).
+  * Window outputs are written by their final GEMMs straight into the accumulated result tensors, and the tail frames
+    the seed decode needs are read from there as strided views: the steady-state step contains no torch kernels.
 """
 from __future__ import annotations
 
@@ -23,7 +25,6 @@ from .. import ops
 PARTS = ("face", "upper", "hands", "lower")
 # WavEncoder geometry P.py:300-307: (stride, first-conv padding, has downsample branch)
 WAV_BLOCKS = ((5, 1600, True), (6, 0, True), (1, 7, False), (6, 0, True), (1, 7, False), (3, 0, True))
-SEED_DECODE_FRAMES = 16
 NHEAD = 4
 
 
@@ -444,9 +445,12 @@ class EmageEngine:
         kv, mem_face = self._fork_audio.run([body, face])
         return mem_face, kv
 
-    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body):
+    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body, dest=None):
         """One window of EmageAudioModel.forward (M.py:265-341) given the hoisted audio tensors.
-        win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows)."""
+        win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows).
+        dest: optional dict name -> (bs, t, 256) fp32 view the final GEMM of that output writes into (the window's rows
+        of inference()'s accumulated outputs), so nothing is copied afterwards."""
+        dest = dest or {}
         bs, t = (win_in.p.batch, win_in.p.rows) if isinstance(win_in, ops.Act) and win_in.f is None else _f32(win_in).shape[:2]
         E = self.E
         spk_f, spk_b = speaker_id_rows
@@ -459,8 +463,8 @@ class EmageEngine:
             x = ops.add_rows(None, self.pe, spk_f, ops.ROW_SPK, ops.ROW_PE, bs, t, E, nsplit=ns)
             for i, layer in enumerate(self.face_dec):
                 x = layer(x, layer.project_memory(mem_f), want="fp" if i + 1 < len(self.face_dec) else "p")
-            rec = self.out_proj["face"](x, want="fp")
-            return {"rec_face": _f32(rec), "cls_face": self.cls["face"](rec)}
+            rec = self.out_proj["face"](x, want="fp", out=dest.get("rec_face"))
+            return {"rec_face": _f32(rec), "cls_face": self.cls["face"](rec, out=dest.get("cls_face"))}
 
         def body_branch():                                                              # M.py:297-330
             hint_body = self.hint_body(hint, want="p" if ns else "f")
@@ -480,8 +484,8 @@ class EmageEngine:
                 tgt = ops.add_rows(lat[p], self.pe, spk_b, ops.ROW_SPK, ops.ROW_NONE, bs, t, E, nsplit=ns)
                 mem = ops.add2(lat[a], lat[b], nsplit=ns, f32=ns == 0)
                 r = layer(tgt, layer.project_memory(mem))
-                rec = self.out_proj[p](ops.add2(lat[p], r, nsplit=ns, f32=ns == 0), want="fp")
-                return {"rec_" + p: _f32(rec), "cls_" + p: self.cls[p](rec)}
+                rec = self.out_proj[p](ops.add2(lat[p], r, nsplit=ns, f32=ns == 0), want="fp", out=dest.get("rec_" + p))
+                return {"rec_" + p: _f32(rec), "cls_" + p: self.cls[p](rec, out=dest.get("cls_" + p))}
 
             out = {}
             for d in self._fork_parts.run([lambda p=p: refine(p) for p in PARTS[1:]]):
@@ -505,12 +509,13 @@ class VQEngine:
     DIMS = {"face": 106, "upper": 78, "hands": 180, "lower": 61}
 
     def __init__(self, sds, cfgs):
-        self.codebook, self.e2, self.decoder, self.encoder = {}, {}, {}, {}
+        self.codebook, self.e2, self.decoder, self.encoder, self.vae_layers = {}, {}, {}, {}, {}
         for p in PARTS:
             sd, cfg = sds[p], cfgs[p]
             self.codebook[p] = sd["quantizer.embedding.weight"].contiguous()
             self.e2[p] = ops.row_sqnorm(self.codebook[p])
             self.decoder[p] = _ConvStack(sd, "decoder", "decoder", int(cfg["vae_layer"]))
+            self.vae_layers[p] = int(cfg["vae_layer"])
             self._enc_args = None
         self.has_global = "global" in sds and sds["global"] is not None
         if self.has_global:
@@ -522,8 +527,8 @@ class VQEngine:
 
     def part_decode(self, p, index=None, latent=None):
         """EmageVQVAEConv.decode / decode_from_latent (M.py:56-70) -> (pose features, indices)."""
-        if index is None:
-            index = ops.l2_argmin(latent.contiguous(), self.codebook[p], self.e2[p])
+        if index is None:                           # latent: (bs, t, 256), dense rows, any clip stride (a window's tail)
+            index = ops.l2_argmin(latent, self.codebook[p], self.e2[p])
         return self.decoder[p](ops.gather_rows(self.codebook[p], index.contiguous(), nsplit=_ns())), index
 
     def decode(self, index, latent, get_global_motion=False, ref_trans=None):
@@ -549,12 +554,23 @@ class VQEngine:
         """M.py:195-205."""
         rec = self.global_dec(self.global_enc(lower_mix))
         bs = rec.shape[0]
+        ref_trans = ref_trans.to(device=rec.device, dtype=torch.float32)
         if ref_trans.dim() == 2:                    # (n,3) -> every clip starts at row 0 (M.py:198-201)
-            ref = ref_trans[0:1].expand(bs, 3)
+            ref = ref_trans[0:1].expand(bs, 3)      # stride-0 view: the kernel takes the clip stride
         else:
             ref = ref_trans[:, 0]
-        ref = ref.to(device=rec.device, dtype=torch.float32).contiguous()
+            if ref.stride(1) != 1:
+                ref = ref.contiguous()
         return ops.global_trans(rec, ref, 1 / 30)
+
+
+def seed_decode_frames(cfg, vq):
+    """Frames of a window's tail the in-loop VQ decode has to produce so that its last `seed_frames` outputs equal a
+    decode of the whole window (M.py:411-418): the part decoders are stacks of k=3 convs - 2 ResBlocks (4 convs),
+    vae_layer convs, 1 output conv - so an output frame sees +-(5 + vae_layer) latent frames (derived from
+    the config instead of a constant 16)."""
+    halo = 5 + max(vq.vae_layers.values())
+    return int(cfg["seed_frames"]) + halo
 
 
 def select_inputs(cfg, out, idx):
@@ -585,15 +601,18 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
     length = n * 30 // 16000                                                             # M.py:345
     window, pre = int(cfg["pose_length"]), int(cfg["seed_frames"])
     ch = int(cfg["pose_dims"]) + 7
-    # default motion = identity rotations (rot6d of zero axis-angle is [1,0,0,0,1,0]) + zero trans/contact
-    motion = torch.zeros(bs, length, ch, device=dev)
-    motion[:, :, 0:ch - 7:6] = 1.0
-    motion[:, :, 4:ch - 7:6] = 1.0
-    if masked_motion is not None:
-        motion[:, :masked_motion.shape[1]] = masked_motion.to(dev)
-    full_mask = torch.ones(bs, length, ch, device=dev)
-    if mask is not None:
-        full_mask[:, :mask.shape[1]] = mask.to(dev)
+    # No masked_motion / mask given (the demo's call): the defaults - identity rotations (rot6d [1,0,0,0,1,0]) + zero
+    # trans / contact, everything masked (M.py:369-377) - are generated inside window_input, no tensors are built.
+    motion = full_mask = None
+    if masked_motion is not None or mask is not None:
+        motion = torch.zeros(bs, length, ch, device=dev)
+        motion[:, :, 0:ch - 7:6] = 1.0
+        motion[:, :, 4:ch - 7:6] = 1.0
+        if masked_motion is not None:
+            motion[:, :masked_motion.shape[1]] = masked_motion.to(dev)
+        full_mask = torch.ones(bs, length, ch, device=dev)
+        if mask is not None:
+            full_mask[:, :mask.shape[1]] = mask.to(dev)
     plan = window_plan(length, window, pre)
     spf = 16000 // 30                                                                    # 533, M.py:393
     if not plan:
@@ -617,22 +636,27 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
             hoisted[first + j] = (mem_face[j], [_window_of(k, j, bs) for k in kv])
 
     out_len = sum(k for _, _, k in plan)
-    acc = {k + p: torch.empty(bs, out_len, 256, device=dev) for k in ("rec_", "cls_") for p in PARTS}
-    seed = motion[:, :pre].contiguous()                                                  # M.py:379
+    # Every window writes its t frames straight into the accumulated outputs at its offset; the `pre` frames beyond the
+    # `keep` it contributes (M.py:419-426) are overwritten by the next window.  Only a full-length LAST window would
+    # spill past the end: `pad` spare rows take that, and the result is the dense [:out_len] prefix (a copy only then).
+    pad = max(0, max(off_t for off_t in [sum(k for _, _, k in plan[:i]) + (e - s) for i, (s, e, _) in enumerate(plan)]) - out_len)
+    acc = {k + p: torch.empty(bs, out_len + pad, 256, device=dev) for k in ("rec_", "cls_") for p in PARTS}
+    seed = None                       # first window: the seed is motion[:, :pre] itself (M.py:379) - window_input keeps it
     off = 0
     for wi, (s, e, keep) in enumerate(plan):
         t = e - s
-        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre, nsplit=_ns(), f32=_ns() == 0)
+        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre, nsplit=_ns(), f32=_ns() == 0,
+                                  shape=(bs, length, ch))
         mem_face, kv = hoisted[wi]
-        out = engine.window(win_in, spk, mem_face, kv)
-        for k in acc:
-            acc[k][:, off:off + keep].copy_(out[k][:, :keep])                           # M.py:419-426,463-470
+        out = engine.window(win_in, spk, mem_face, kv, dest={k: v[:, off:off + t] for k, v in acc.items()})
         off += keep
         if wi + 1 < len(plan):                                                           # seed for the next window
-            nd = min(t, SEED_DECODE_FRAMES)
-            tail = {k: v[:, t - nd:].contiguous() for k, v in out.items()}
+            nd = min(t, seed_decode_frames(cfg, vq))
+            tail = {k: v[:, t - nd:] for k, v in out.items()}                            # strided views, read in place
             idx = {p: ops.row_argmax(tail["cls_" + p]) for p in PARTS}                   # M.py:398-401
             index, latent = select_inputs(cfg, tail, idx)
             dec = vq.decode(index, latent)
-            seed = dec["all_motion4inference"][:, nd - pre:].contiguous()                # M.py:418
+            seed = dec["all_motion4inference"][:, nd - pre:]                             # M.py:418
+    if pad:
+        acc = {k: v[:, :out_len].contiguous() for k, v in acc.items()}
     return acc

@@ -395,7 +395,7 @@ class EmageAudioModel(_EngineOwner):
         bs, t, ch = motion.shape
         # no seed splice here: pre = 0 makes window_input the plain `where(mask==1, embedding, motion)`
         ns = E._ns()
-        win_in = ops.window_input(motion, mask, motion[:, :0].contiguous(), eng.mask_embedding, 0, t, 0,
+        win_in = ops.window_input(motion, mask, None, eng.mask_embedding, 0, t, 0,
                                   nsplit=ns, f32=ns == 0)
         mem_face, kv = eng.audio_phase(audio, 0, 0, 1, audio.shape[1], t)
         return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv)

@@ -137,7 +137,11 @@ def _new_planes(nsplit, lead_shape, ch, device, slack_rows=0, dtype=None):
     ld = _round_up(ch, 8)
     if slack_rows:
         buf = torch.empty(nsplit, batch * rows + slack_rows, ld, device=device, dtype=dtype)
-        buf[:, batch * rows:].zero_()
+        if buf.is_cuda:
+            for i in range(nsplit):               # cudaMemsetAsync: a memset node under graph capture, not a kernel
+                _lib.call("pm_memset_async", buf[i, batch * rows:].data_ptr(), 0, slack_rows * ld * buf.element_size(), _stream())
+        else:
+            buf[:, batch * rows:].zero_()
         t = buf[:, :batch * rows].view(nsplit, batch, rows, ld)
     else:
         t = torch.empty(nsplit, batch, rows, ld, device=device, dtype=dtype)
@@ -217,45 +221,77 @@ def add2(a, b, nsplit=0, f32=True):
     return _result(out, pl, nsplit)
 
 
-def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True):
-    _chk(motion), _chk(mask), _chk(seed)
-    assert motion.is_contiguous() and mask.is_contiguous() and seed.is_contiguous()
-    batch, total_len, ch = motion.shape
-    assert mask.shape == motion.shape and seed.shape == (batch, pre, ch)
-    out = torch.empty(batch, win_len, ch, device=motion.device, dtype=torch.float32) if (f32 or not nsplit) else None
-    pl = _new_planes(nsplit, (batch, win_len), ch, motion.device) if nsplit else None
-    _call("pm_window_input_f32", motion.data_ptr(), mask.data_ptr(), seed.data_ptr(), mask_embedding.data_ptr(),
-          _ptr(out), batch, total_len, start, win_len, pre, ch, *_pargs(pl), _stream())
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True, shape=None):
+    """motion / mask: (batch, total_len, ch) or None = inference()'s defaults (then `shape` = (batch, total_len, ch));
+    seed: (batch, pre, ch) view with dense rows (any clip stride), None when pre == 0."""
+    batch, total_len, ch = motion.shape if motion is not None else shape
+    for t in (motion, mask):
+        if t is not None:
+            _chk(t)
+            assert t.is_contiguous() and t.shape == (batch, total_len, ch)
+    seed_bs = 0
+    if seed is not None:
+        _chk(seed)
+        assert seed.shape == (batch, pre, ch) and (pre <= 1 or seed.stride(1) == ch)
+        seed_bs = seed.stride(0)
+    dev = mask_embedding.device
+    out = torch.empty(batch, win_len, ch, device=dev, dtype=torch.float32) if (f32 or not nsplit) else None
+    pl = _new_planes(nsplit, (batch, win_len), ch, dev) if nsplit else None
+    _call("pm_window_input_f32", _ptr(motion), _ptr(mask), _ptr(seed), mask_embedding.data_ptr(),
+          _ptr(out), batch, total_len, start, win_len, pre, ch, seed_bs, *_pargs(pl), _stream())
     return _result(out, pl, nsplit)
+
+
+def _batched_rows(x, ld):
+    """(rows, rows_per_batch, batch stride) of a (rows, ch) matrix or a (batch, rows, ch) view whose rows are `ld` apart."""
+    if x.dim() == 2:
+        assert x.stride(0) == ld
+        return x.shape[0], 0, 0
+    assert x.dim() == 3 and (x.shape[1] == 1 or x.stride(1) == ld)
+    return x.shape[0] * x.shape[1], x.shape[1], x.stride(0)
 
 
 def l2_argmin(z, codebook, e2, engine="auto", max_ctas=0):
     """fp32 argmin_k |z - e_k|^2, first minimum wins.  engine: "auto" (the product path: tcgen05 screen + exact fp32
     re-scoring for 256-code codebooks, fp32 SIMT otherwise), "tc" or "simt" (tests / microbenchmarks)."""
     _chk(z), _chk(codebook), _chk(e2)
-    assert z.is_contiguous() and codebook.is_contiguous()
-    rows = z.numel() // z.shape[-1]
-    idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
+    assert codebook.is_contiguous()
     n_codes, e_dim = codebook.shape
+    if z.dim() > 3:
+        z = z.reshape(-1, e_dim)
+    rows, rpb, z_bs = _batched_rows(z, e_dim)      # (rows, 256) or a (batch, rows, 256) view, e.g. the tail of a window
+    idx = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64)
     if engine == "tc":
-        _call("pm_l2_argmin_tc", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim, idx.data_ptr(),
-              int(max_ctas), _stream())
+        _call("pm_l2_argmin_tc", z.data_ptr(), rows, rpb, z_bs, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim,
+              idx.data_ptr(), int(max_ctas), _stream())
     elif engine == "simt":
-        _call("pm_l2_argmin_simt_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim,
+        _call("pm_l2_argmin_simt_f32", z.data_ptr(), rows, rpb, z_bs, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim,
               idx.data_ptr(), _stream())
     else:
-        _call("pm_l2_argmin_f32", z.data_ptr(), rows, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim, idx.data_ptr(),
-              _stream())
+        _call("pm_l2_argmin_f32", z.data_ptr(), rows, rpb, z_bs, codebook.data_ptr(), e2.data_ptr(), n_codes, e_dim,
+              idx.data_ptr(), _stream())
     return idx
 
 
-def row_argmax(x):
+def row_argmax(x, nonfinite=None):
+    """First argmax over the last dim of a (rows, ch) matrix or a (batch, rows, ch) view (any clip stride).
+    nonfinite: optional int32[1] device flag, set to 1 when a NaN / inf is read (never cleared here)."""
     _chk(x)
-    assert x.is_contiguous()
     ch = x.shape[-1]
+    if x.dim() > 3:
+        x = x.reshape(-1, ch)
+    ld = x.stride(-2) if x.shape[-2] > 1 else ch
+    rows, rpb, x_bs = _batched_rows(x, ld)
     idx = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int64)
-    _call("pm_row_argmax_f32", x.data_ptr(), x.numel() // ch, ch, ch, idx.data_ptr(), _stream())
+    _call("pm_row_argmax_f32", x.data_ptr(), rows, ch, ld, rpb, x_bs, idx.data_ptr(), _ptr(nonfinite), _stream())
     return idx
+
+
+def zero_flag(device):
+    """int32[1] device flag cleared by a memset node (no kernel)."""
+    flag = torch.empty(1, device=device, dtype=torch.int32)
+    _lib.call("pm_memset_async", flag.data_ptr(), 0, 4, _stream())
+    return flag
 
 
 def gather_rows(codebook, index, nsplit=0, f32=True):
@@ -294,12 +330,12 @@ def pose_compose(face, upper, hands, lower, bs, t, device):
 
 def global_trans(rec, ref_trans, dt, vel_off=54):
     _chk(rec), _chk(ref_trans)
-    assert rec.is_contiguous() and ref_trans.is_contiguous()
+    assert rec.is_contiguous()
     bs, t, ld = rec.shape
-    assert ref_trans.shape == (bs, 3)
+    assert ref_trans.shape == (bs, 3)                      # may be an expanded (stride 0) view of one row
     trans = torch.empty(bs, t, 3, device=rec.device, dtype=torch.float32)
-    _call("pm_global_trans_f32", rec.data_ptr(), ld, vel_off, ref_trans.data_ptr(), float(dt), trans.data_ptr(),
-          bs, t, _stream())
+    _call("pm_global_trans_f32", rec.data_ptr(), ld, vel_off, ref_trans.data_ptr(), ref_trans.stride(0), float(dt),
+          trans.data_ptr(), bs, t, _stream())
     return trans
 
 

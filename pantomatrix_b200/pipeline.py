@@ -13,12 +13,6 @@ _OVERFLOW = ("fp16x3: a GEMM operand exceeded the fp16 range (|x| > 65504) and t
              "rerun with engine.set_precision('bf16x6')")
 
 
-def _finite_flag(lat):
-    """0-d bool device tensor: every latent / logit is finite.  fp16 operand planes turn an out-of-range activation
-    into inf - inf = NaN in the consuming GEMM; NaN reaches these tensors, so one reduction guards the whole step."""
-    return torch.stack([torch.isfinite(lat[k]).all() for k in sorted(lat)]).all()
-
-
 @torch.no_grad()
 def generate(model, motion_vq, audio, speaker_id=None, masked_motion=None, mask=None, ref_trans=None):
     """audio (bs, n) float32 16 kHz.  Returns (latent_dict, pred_dict) like T.py:32 and T.py:44-47."""
@@ -27,14 +21,15 @@ def generate(model, motion_vq, audio, speaker_id=None, masked_motion=None, mask=
     if speaker_id is None:
         speaker_id = torch.zeros(bs, 1, dtype=torch.long, device=dev)                  # T.py:19
     lat = model.inference(audio, speaker_id, motion_vq, masked_motion=masked_motion, mask=mask)
-    generate.finite = None
-    if ops.plane_format() == "fp16":
-        generate.finite = _finite_flag(lat)
-        capturing = lat["rec_face"].is_cuda and torch.cuda.is_current_stream_capturing()
-        if not capturing and not bool(generate.finite):
-            raise _lib.PmError(_OVERFLOW)
+    # fp16 operand planes turn an out-of-range activation into inf - inf = NaN in the consuming GEMM; a NaN anywhere
+    # upstream reaches the logits (cls_* = MLP(rec_*)), which the argmax kernels read anyway: they raise the flag.
+    generate.nonfinite = ops.zero_flag(dev) if ops.plane_format() == "fp16" else None
     cfg = model.cfg.to_dict()
-    idx = {p: ops.row_argmax(lat["cls_" + p]) for p in PARTS}                          # T.py:39-42
+    idx = {p: ops.row_argmax(lat["cls_" + p], nonfinite=generate.nonfinite) for p in PARTS}       # T.py:39-42
+    if generate.nonfinite is not None:
+        capturing = lat["rec_face"].is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing and bool(generate.nonfinite):
+            raise _lib.PmError(_OVERFLOW)
     index, latent = select_inputs(cfg, lat, idx)
     if ref_trans is None:
         ref_trans = torch.zeros(1, 3, device=dev)                                       # trans[:,0], T.py:30,47
@@ -45,7 +40,7 @@ def generate(model, motion_vq, audio, speaker_id=None, masked_motion=None, mask=
     return lat, pred
 
 
-generate.finite = None
+generate.nonfinite = None
 
 
 class CapturedPipeline:
@@ -76,7 +71,7 @@ class CapturedPipeline:
         with torch.cuda.graph(self.graph):
             self.latent, self.pred = generate(model, motion_vq, self.audio, self.speaker_id, ref_trans=self.ref_trans)
         self.kernels_per_replay = ops.launch_count - before
-        self.finite = generate.finite                        # fp16 planes only: in-graph overflow flag (else None)
+        self.nonfinite = generate.nonfinite                  # fp16 planes only: in-graph overflow flag (else None)
 
     @torch.no_grad()
     def __call__(self, audio, speaker_id=None):
@@ -86,6 +81,6 @@ class CapturedPipeline:
             self.speaker_id.copy_(speaker_id, non_blocking=True)
         self.graph.replay()
         ops.launch_count += self.kernels_per_replay
-        if self.finite is not None and not bool(self.finite):       # one 1-byte read back per step (fp16 planes only)
+        if self.nonfinite is not None and bool(self.nonfinite):     # one 4-byte read back per step (fp16 planes only)
             raise _lib.PmError(_OVERFLOW)
         return self.latent, self.pred

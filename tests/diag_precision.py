@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from helpers import build_product  # noqa: E402
+from synthetic_models import build_product  # noqa: E402
 from oracle import emage_oracle as O  # noqa: E402
 from oracle.weights import make_checkpoint, synth_audio  # noqa: E402
 from pantomatrix_b200.pipeline import generate  # noqa: E402

@@ -108,10 +108,17 @@ def add2(a, b, nsplit=0, f32=True):
     return _res(a + b, nsplit, f32)
 
 
-def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True):
+def window_input(motion, mask, seed, mask_embedding, start, win_len, pre, nsplit=0, f32=True, shape=None):
+    if motion is None:                                   # inference()'s defaults (M.py:369-377)
+        motion = torch.zeros(shape)
+        motion[:, :, 0:shape[2] - 7:6] = 1.0
+        motion[:, :, 4:shape[2] - 7:6] = 1.0
+    if mask is None:
+        mask = torch.ones(motion.shape)
     wm, wk = motion[:, start:start + win_len].clone(), mask[:, start:start + win_len].clone()
     if pre:
-        wm[:, :pre] = torch.where(wk[:, :pre] == 0, motion[:, start:start + pre], seed)
+        if seed is not None:
+            wm[:, :pre] = torch.where(wk[:, :pre] == 0, motion[:, start:start + pre], seed)
         wk[:, :pre] = 0
     return _res(torch.where(wk == 1, mask_embedding.view(1, 1, -1).expand_as(wm), wm), nsplit, f32)
 
@@ -122,8 +129,14 @@ def l2_argmin(z, codebook, e2, engine="auto", max_ctas=0):
     return d.argmin(1).reshape(z.shape[:-1])
 
 
-def row_argmax(x):
+def row_argmax(x, nonfinite=None):
+    if nonfinite is not None and not bool(torch.isfinite(x).all()):
+        nonfinite.fill_(1)
     return x.argmax(-1)
+
+
+def zero_flag(device):
+    return torch.zeros(1, dtype=torch.int32)
 
 
 def gather_rows(codebook, index, nsplit=0, f32=True):

@@ -84,7 +84,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pm_emage.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().pm_abi_version() == 3
+    assert _lib.load().pm_abi_version() == 4
 
 
 def test_ctypes_signatures_match_the_header():
@@ -131,7 +131,8 @@ def test_ops_call_sites_pass_the_declared_number_of_arguments():
             n = sum(4 if isinstance(a, ast.Starred) else 1 for a in node.args[1:])
             assert n == len(_lib.SIGNATURES[name]), (name, n, len(_lib.SIGNATURES[name]))
             seen.add(name)
-    assert seen == set(_lib.SIGNATURES) - {"pm_abi_version", "pm_device_cc"}, seen ^ set(_lib.SIGNATURES)
+    # pm_memset_async is not a kernel launch: ops.py reaches it through _lib.call, not through the counting _call
+    assert seen == set(_lib.SIGNATURES) - {"pm_abi_version", "pm_device_cc", "pm_memset_async"}, seen ^ set(_lib.SIGNATURES)
 
 
 def test_ops_wrappers_marshal_valid_arguments(monkeypatch):

@@ -7,7 +7,6 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import EXPERIMENTAL  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -276,6 +275,46 @@ def test_l2_argmin_million_rows_optimality(ops):
         assert bool((picked - d.min(1).values < 5e-3).all())
 
 
+def test_window_input_defaults_and_strided_seed(ops):
+    """motion / mask = None generate inference()'s defaults in the kernel (identity rot6d + zero trans/contact, all
+    masked); the seed is read in place from the tail of a longer decode (clip stride != pre * ch); no seed at all
+    (first window) keeps motion[:, :pre]."""
+    bs, total, ch, pre = 3, 130, 337, 4
+    emb = _rand(ch, seed=70)
+    motion = torch.zeros(bs, total, ch, device="cuda")
+    motion[:, :, 0:ch - 7:6] = 1.0
+    motion[:, :, 4:ch - 7:6] = 1.0
+    mask = torch.ones_like(motion)
+    dec = _rand(bs, 13, ch, seed=71)                                     # a 13-frame seed decode; its last 4 frames are the seed
+    seed = dec[:, 13 - pre:]
+    want = ops.window_input(motion, mask, seed.contiguous(), emb, 60, 64, pre)
+    got = ops.window_input(None, None, seed, emb, 60, 64, pre, shape=(bs, total, ch))
+    assert torch.equal(got, want)
+    first = ops.window_input(None, None, None, emb, 0, 64, pre, shape=(bs, total, ch))
+    assert torch.equal(first, ops.window_input(motion, mask, motion[:, :pre].contiguous(), emb, 0, 64, pre))
+    user = _rand(bs, total, ch, seed=72)                                 # caller-supplied motion with the same strided seed
+    assert torch.equal(ops.window_input(user, mask, seed, emb, 60, 64, pre), ops.window_input(user, mask, seed.contiguous(), emb, 60, 64, pre))
+
+
+def test_strided_tail_views_and_nonfinite_flag(ops):
+    """row_argmax / l2_argmin on the last frames of a window read in place (clip stride = whole sequence), and the
+    non-finite flag the fp16x3 pipeline relies on."""
+    bs, total, nd = 5, 300, 13
+    x = _rand(bs, total, 256, seed=73)
+    tail = x[:, 64 - nd:64]
+    assert torch.equal(ops.row_argmax(tail), tail.contiguous().argmax(-1))
+    cb = _rand(256, 256, seed=74)
+    e2 = ops.row_sqnorm(cb)
+    for engine in ENGINES:
+        assert torch.equal(ops.l2_argmin(tail, cb, e2, engine=engine), ops.l2_argmin(tail.contiguous(), cb, e2, engine=engine))
+    flag = ops.zero_flag("cuda")
+    ops.row_argmax(tail, nonfinite=flag)
+    assert int(flag) == 0
+    x[2, 60, 7] = float("inf")
+    ops.row_argmax(tail, nonfinite=flag)
+    assert int(flag) == 1
+
+
 def test_row_argmax_first_max(ops):
     x = _rand(9600, 256, seed=36)
     x[5, 17] = x[5, 200] = 50.0                      # tie -> first index
@@ -328,6 +367,8 @@ def test_global_trans_sequential_sum(ops):
     bs, t = 4, 300
     rec, ref = _rand(bs, t, 61, seed=43), _rand(bs, 3, seed=44)
     got = ops.global_trans(rec, ref, 1 / 30).cpu()
+    assert torch.equal(ops.global_trans(rec, ref[0:1].expand(rec.shape[0], 3), 1 / 30),
+                       ops.global_trans(rec, ref[0:1].expand(rec.shape[0], 3).contiguous(), 1 / 30))   # stride-0 ref
     v = rec.cpu()[:, :, 54:57]
     x, z = [ref.cpu()[:, 0:1]], [ref.cpu()[:, 2:3]]
     for i in range(1, t):                                        # P.py:107-115
@@ -383,15 +424,3 @@ def test_fused_plane_outputs(ops, nsplit, plane_format):
     ref = ops.window_input(motion, mask, seed, emb, 60, 64, 4)
     got = ops.window_input(motion, mask, seed, emb, 60, 64, 4, nsplit=nsplit, f32=False)
     assert got.p.t.shape[-1] == 344 and (_planes_value(got.p) - ref).abs().max() <= tol * ref.abs().max()
-
-
-@EXPERIMENTAL
-def test_attention_mma_variant_in_subprocess():
-    """The attention tests again with PM_ATTN_MMA=1 (mma.sync 3xTF32 kernel); the knob is read once per process."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, PM_ATTN_MMA="1", PM_TEST_EXPERIMENTAL="0")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu",
-                        "-k", "attention or fused_plane"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:]

@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import build_product  # noqa: E402
+from synthetic_models import build_product  # noqa: E402
 from oracle.weights import synth_audio  # noqa: E402
 from pantomatrix_b200.emage_audio import engine  # noqa: E402
 from pantomatrix_b200.pipeline import generate  # noqa: E402
