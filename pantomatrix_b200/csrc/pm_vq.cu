@@ -27,8 +27,12 @@ __global__ void __launch_bounds__(NT) l2_argmin_kernel(
   for (int i = tid; i < RT * (ED / 4); i += NT) {          // coalesced float4 loads of the z tile
     const int r = i / (ED / 4), c4 = i % (ED / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < rows)
-      v = *reinterpret_cast<const float4*>(z + ((r0 + r) / rows_per_batch) * z_bs + ((r0 + r) % rows_per_batch) * ED + c4 * 4);
+    if (r0 + r < rows) {
+      const unsigned g = (unsigned)(r0 + r), gb = g / (unsigned)rows_per_batch;      // strided views are small (host checks)
+      const float* zr = rows_per_batch == 0x7fffffff ? z + (r0 + r) * ED
+                                                     : z + (long long)gb * z_bs + (long long)(g - gb * (unsigned)rows_per_batch) * ED;
+      v = *reinterpret_cast<const float4*>(zr + c4 * 4);
+    }
     float* d = Zs + r * EDP + c4 * 4;
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(256) row_argmax_kernel(const float* __restrict
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* __restrict__ xr = x + (row / rows_per_batch) * x_bs + (row % rows_per_batch) * ldx;
+  const unsigned rb = (unsigned)row / (unsigned)rows_per_batch;            // strided views are small (host checks)
+  const float* __restrict__ xr = rows_per_batch == 0x7fffffff ? x + row * ldx
+                                                              : x + (long long)rb * x_bs + (long long)((unsigned)row - rb * (unsigned)rows_per_batch) * ldx;
   float best = -INFINITY;
   int bk = 0x7fffffff;
   bool bad = false;
@@ -163,8 +169,8 @@ extern "C" int pm_l2_argmin_simt_f32(const float* z, long long rows, int rows_pe
                                      const float* codebook, const float* e2,
                                      int n_codes, int e_dim, long long* index, void* stream) {
   PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
-  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; z_bs = 0; }
-  PM_REQUIRE((z_bs & 3) == 0);
+  if (rows_per_batch <= 0 || z_bs == (long long)rows_per_batch * ED) { rows_per_batch = 0x7fffffff; z_bs = 0; }
+  PM_REQUIRE((z_bs & 3) == 0 && (rows_per_batch == 0x7fffffff || rows < 0x7fffffffLL));
   if (e_dim != ED || n_codes <= 0 || n_codes % CT != 0) return PM_EUNSUPPORTED;
   if (rows == 0) return PM_OK;
   {   // per device, cheap: no process-wide "configured" flag (a second GPU in the same process needs it too)
@@ -192,7 +198,8 @@ extern "C" int pm_row_argmax_f32(const float* x, long long rows, int ch, int ldx
                                  long long* index, int* nonfinite, void* stream) {
   PM_REQUIRE(x && index && rows >= 0 && ch > 0 && ldx >= ch);
   if (rows == 0) return PM_OK;
-  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; x_bs = 0; }      // one dense (rows, ldx) matrix
+  if (rows_per_batch <= 0 || x_bs == (long long)rows_per_batch * ldx) { rows_per_batch = 0x7fffffff; x_bs = 0; }   // dense (rows, ldx)
+  PM_REQUIRE(rows_per_batch == 0x7fffffff || rows < 0x7fffffffLL);
   row_argmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, ch, ldx, rows_per_batch, x_bs,
                                                                                   index, nonfinite);
   PM_LAUNCH_CHECK();

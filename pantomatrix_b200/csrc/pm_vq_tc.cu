@@ -8,12 +8,13 @@
 // error are re-scored in exact fp32 (same expression and tie rule as the SIMT kernel).  The emitted index is
 // therefore the fp32 argmin for every row, while each row's 1 KB is read from HBM once.
 //
-// Persistent kernel, one CTA per SM, 416 threads:
+// Persistent kernel, one CTA per SM, 544 threads:
 //   warps 0-7   loaders    - coalesced float4 loads of 8 full rows per warp and batch (16 x 16 B in flight per thread),
 //                            per-row max / sum of squares by warp shuffle, power-of-two row scaling into the fp16
 //                            range, fp16 conversion into the 128B-swizzled K-major UMMA layout
 //   warp  8     MMA issuer - 16 x tcgen05.mma (M=128, N=256, K=16) per tile into one of two TMEM accumulators
-//   warps 9-12  epilogue   - tcgen05.ld, screened distances d~ = e2[k] - 2 z.e (row scale folded into the FMA),
+//   warps 9-16  epilogue   - two groups of four warps taking alternate tiles (group = TMEM accumulator), each:
+//                            tcgen05.ld, screened distances d~ = e2[k] - 2 z.e (row scale folded into the FMA),
 //                            pass 1: minimum, pass 2: every k within tau of it; rows with more than one candidate
 //                            are re-scored in fp32 by the whole warp (8 lanes per candidate, shuffle reduction)
 // The fp16 codebook (128 KB, scaled by a power of two) stays resident in shared memory for the CTA's lifetime.
@@ -31,11 +32,11 @@ namespace {
 constexpr int ED = 256;                 // e_dim
 constexpr int NC = 256;                 // codes
 constexpr int TM = 128;                 // rows per tile (UMMA M)
-constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 4;      // epilogue = warps 9..12
+constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 8;      // epilogue = warps 9..16: two groups of four, one per TMEM accumulator
 constexpr int NTHREADS = 32 * (LOAD_WARPS + 1 + EPI_WARPS);     // 416
 constexpr int KB_A = TM * 128;          // bytes of one 64-channel k-block of the z tile (16 KB)
 constexpr int KB_B = NC * 128;          // ... of the codebook (32 KB)
-constexpr int MAXC = 8;                 // extra candidates kept per row; a full list means "re-score every code"
+constexpr int MAXC = 8;                 // candidates kept per row (the screen's minimum included); more = "re-score every code"
 constexpr int SLOTS = 4;                // ring of per-tile row info (loaders run at most 2 tiles ahead of the epilogue)
 
 // Instrumented build only (-DPM_VQ_TIMING, tools/vq_timeline.py): clock64 cycles CTA 0 spends per phase.
@@ -61,8 +62,8 @@ struct Smem {
   static constexpr int A = B + 4 * KB_B;                    // fp16 z tile, 4 k-blocks
   static constexpr int E2 = A + 4 * KB_A;                   // float[256]
   static constexpr int INFO = E2 + NC * 4;                  // float2[SLOTS][TM]: (fma multiplier, tau)
-  static constexpr int CAND = INFO + SLOTS * TM * 8;        // uint8[TM][MAXC]
-  static constexpr int BARS = CAND + TM * MAXC;             // mbarriers
+  static constexpr int CAND = INFO + SLOTS * TM * 8;        // uint8[2 groups][TM][MAXC]
+  static constexpr int BARS = CAND + 2 * TM * MAXC;         // mbarriers
   static constexpr int N_BARS = 2 + 2 + 2 + SLOTS;          // a_full, a_empty, acc_full[2], acc_empty[2], info_full[SLOTS]
   static constexpr int MISC = BARS + N_BARS * 8;            // tmem slot, emax
   static constexpr int TOTAL = MISC + 16;
@@ -73,6 +74,24 @@ __device__ __forceinline__ uint32_t sw128(int row, int byte_in_row) {      // of
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -95,14 +114,20 @@ __device__ __forceinline__ int scale_exp(float m) {
 __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     const float* __restrict__ z, long long rows, int rows_per_batch, long long z_bs, const float* __restrict__ codebook,
     const float* __restrict__ e2, long long* __restrict__ index) {
-  // row g of the (batch, rows_per_batch, 256) view: z + (g / rows_per_batch) * z_bs + (g % rows_per_batch) * 256
-  auto row_ptr = [&](long long g) { return z + (g / rows_per_batch) * z_bs + (g % rows_per_batch) * ED; };
+  // row g of the (batch, rows_per_batch, 256) view: z + (g / rows_per_batch) * z_bs + (g % rows_per_batch) * 256.
+  // rows_per_batch == 0 marks one dense matrix (the host folds dense views into it): no division on the hot path,
+  // and the strided case (a window's tail frames: a few hundred rows) divides in 32 bits.
+  auto row_ptr = [&](long long g) -> const float* {
+    if (rows_per_batch == 0) return z + g * ED;
+    const unsigned gb = (unsigned)g / (unsigned)rows_per_batch, gl = (unsigned)g - gb * (unsigned)rows_per_batch;
+    return z + (long long)gb * z_bs + (long long)gl * ED;
+  };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sm_u = smem_u32(sm);
   float* e2s = reinterpret_cast<float*>(sm + Smem::E2);
-  float2* info = reinterpret_cast<float2*>(sm + Smem::INFO);
-  uint8_t* cands = sm + Smem::CAND;
+  const uint32_t e2s_u = sm_u + Smem::E2, info_u = sm_u + Smem::INFO, cands_u = sm_u + Smem::CAND;   // shared-space addresses:
+  // every hot access below is an explicit ld/st.shared (generic pointers cost a 64-bit address computation each)
   const uint32_t bars = sm_u + Smem::BARS;
   const uint32_t a_full = bars, a_empty = bars + 8, acc_full = bars + 16, acc_empty = bars + 32, info_full = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::MISC);
@@ -116,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
   if (tid == 0) {
     mbar_init(a_full, LOAD_WARPS);
     mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, EPI_WARPS / 2); }
     for (int s = 0; s < SLOTS; ++s) mbar_init(info_full + 8 * s, LOAD_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
             // d~ = e2[k] + mult * acc ;  tau = 2 B + fp32 slack (covers the exact path's own rounding and flushes)
             const float mult = -2.0f * pow2i(-s) * inv_cb;
             const float tau = 2.0f * bound_c * sqrtf(ss[j]) + 2.4e-7f * 16.f * (ss[j] + e2max);
-            info[slot * TM + r] = make_float2(mult, tau);
+            sts64(info_u + (uint32_t)(slot * TM + r) * 8, __float_as_uint(mult), __float_as_uint(tau));
           }
         }
         if (warp == 0) VQ_ADD(2, t_cv);
@@ -249,15 +274,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     }
   } else {
     // ===== epilogue: TMEM lane quarter = warp % 4, thread = one row of the tile =====
+    // The epilogue is the longest stage of the pipeline (two passes over 256 columns + re-scoring), so two groups of
+    // four warps take alternate tiles: group = TMEM accumulator buffer, no communication between the groups.
     const int q = warp & 3;
+    const int grp = (warp - (MMA_WARP + 1)) >> 2;
     const int trow = q * 32 + lane;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const uint32_t cands_g = cands_u + (uint32_t)(grp * TM * MAXC);
+    int it = grp;
+    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < n_tiles; tile += 2LL * gridDim.x, it += 2) {
       const int buf = it & 1, slot = it & (SLOTS - 1);
       const long long g = tile * TM + trow;
       VQ_T(t_e0);
       mbar_wait(info_full + 8 * slot, (uint32_t)((it >> 2) & 1));
-      const float2 inf = info[slot * TM + trow];
+      const float2 inf = lds64f(info_u + (uint32_t)(slot * TM + trow) * 8);
       mbar_wait(acc_full + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (warp == MMA_WARP + 1) VQ_ADD(6, t_e0);
@@ -271,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       auto reduce_chunk = [&](const uint32_t (&acc)[32], int c0) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
+          const float4 e = lds128(e2s_u + (uint32_t)(c0 + 4 * j4) * 4);
           const float d0 = fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), d1 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y);
           const float d2 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), d3 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w);
           if (d0 < mm[0]) { mm[0] = d0; kk[0] = c0 + 4 * j4; }
@@ -297,32 +326,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         if (mm[u] < m1 || (mm[u] == m1 && kk[u] < k1)) { m1 = mm[u]; k1 = kk[u]; }
       if (warp == MMA_WARP + 1) VQ_ADD(7, t_e1);
       VQ_T(t_e2);
-      // pass 2: every other code within tau of the minimum
+      // pass 2: every code within tau of the minimum (the minimum itself included: nc >= 1)
       const float thr = m1 + inf.y;
       int nc = 0;
-      uint8_t* my = cands + trow * MAXC;
+      const uint32_t my = cands_g + (uint32_t)(trow * MAXC);
+      // The fully unrolled body stays tiny and branch-free: FFMA + compare + one predicated bit-set per code.  The
+      // (rare) hits of a 32-code chunk are then appended to the row's list by a short rolled loop.  Anything bigger
+      // inline makes the pass instruction-fetch / issue bound (13 000 instead of ~1 500 cycles per tile, measured).
       auto collect_chunk = [&](const uint32_t (&acc)[32], int c0) {
+        uint32_t hits = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 e = *reinterpret_cast<const float4*>(e2s + c0 + 4 * j4);
-          const float d[4] = {fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y),
-                              fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w)};
-          if (d[0] <= thr || d[1] <= thr || d[2] <= thr || d[3] <= thr) {       // rare: one branch per four codes
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int k = c0 + 4 * j4 + u;
-              if (d[u] <= thr && k != k1) {
-                if (nc < MAXC) {
-                  my[nc] = (uint8_t)k;
-                  // this row will be re-scored after the pass: pull its operands into L1 now (the re-scoring loop
-                  // was a chain of L2 round trips, ~2300 cycles per row; profiles/vq_timeline_r2.md)
-                  if (nc == 0 && g < rows) { prefetch_row(row_ptr(g)); prefetch_row(codebook + (long long)k1 * ED); }
-                  prefetch_row(codebook + (long long)k * ED);
-                }
-                ++nc;
-              }
-            }
-          }
+          const float4 e = lds128(e2s_u + (uint32_t)(c0 + 4 * j4) * 4);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x) <= thr) hits |= 1u << (4 * j4);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y) <= thr) hits |= 1u << (4 * j4 + 1);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z) <= thr) hits |= 1u << (4 * j4 + 2);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w) <= thr) hits |= 1u << (4 * j4 + 3);
+        }
+#pragma unroll 1
+        while (hits) {
+          const int j = __ffs(hits) - 1;
+          hits &= hits - 1;
+          sts8(my + (uint32_t)(nc & (MAXC - 1)), (uint32_t)(c0 + j));
+          ++nc;
         }
       };
 #pragma unroll 1
@@ -340,25 +366,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+      const bool flagged = nc > 1 && g < rows;            // more than one code within the screen's error bound
+      if (flagged && nc <= MAXC) {                        // pull the operands of the re-scoring into L1 meanwhile
+        prefetch_row(row_ptr(g));
+#pragma unroll 1
+        for (int i = 0; i < nc; ++i) prefetch_row(codebook + (long long)lds8(my + i) * ED);
+      }
 
-      // ---- exact fp32 re-scoring of rows with more than one candidate: whole warp per row, 8 lanes per code ----
-      unsigned need = __ballot_sync(0xffffffffu, nc > 0 && g < rows);
+      // ---- exact fp32 re-scoring of rows with more than one candidate.  Two rows per round (one per half warp: the
+      // loop is a chain of memory round trips, so two independent chains run for the price of one), two candidates at
+      // a time per row (8 lanes each: 32 elements per lane, xor-shuffle reduction - a fixed summation order). ----
+      unsigned need = __ballot_sync(0xffffffffu, flagged);
 #ifdef PM_VQ_TIMING
       {
         const unsigned over = __ballot_sync(0xffffffffu, nc > MAXC);
         if (warp == MMA_WARP + 1) { VQ_CNT(12, __popc(need)); VQ_CNT(13, __popc(over)); }
       }
 #endif
-      const int grp = lane >> 3, gl = lane & 7;
+      const int lg = (lane >> 3) & 1, gl = lane & 7;
       while (need) {
-        const int src = __ffs(need) - 1;
+        const int sa = __ffs(need) - 1;
         need &= need - 1;
+        int sb = sa;
+        if (need) { sb = __ffs(need) - 1; need &= need - 1; }
+        const int src = (lane & 16) ? sb : sa;                           // the row this half warp re-scores
         const int nsrc = __shfl_sync(0xffffffffu, nc, src);
-        const int ksrc = __shfl_sync(0xffffffffu, k1, src);
         const bool all = nsrc > MAXC;                                    // list overflowed: every code is a candidate
-        const int ncand = all ? NC : nsrc + 1;
-        const long long gr = tile * TM + q * 32 + src;
-        const float4* zr = reinterpret_cast<const float4*>(row_ptr(gr));
+        const int ncand = all ? NC : nsrc;
+        const int nmax = max(__shfl_sync(0xffffffffu, ncand, 0), __shfl_sync(0xffffffffu, ncand, 16));
+        const float4* zr = reinterpret_cast<const float4*>(row_ptr(tile * TM + q * 32 + src));
         float4 zv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) zv[i] = __ldg(zr + gl + 8 * i);
@@ -370,11 +406,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         z2 += __shfl_xor_sync(0xffffffffu, z2, 4);
         float best = INFINITY;
         int bk = NC;                                                     // NC = "nothing yet" (loses every tie)
-        const uint8_t* list = cands + (q * 32 + src) * MAXC;
-        for (int base = 0; base < ncand; base += 4) {
-          const int ci = base + grp;
+        const uint32_t list = cands_g + (uint32_t)((q * 32 + src) * MAXC);
+#pragma unroll 1
+        for (int base = 0; base < nmax; base += 2) {
+          const int ci = base + lg;
           const bool valid = ci < ncand;
-          const int c = !valid ? ksrc : (all ? ci : (ci == 0 ? ksrc : (int)list[ci - 1]));
+          const int c = all ? (ci & (NC - 1)) : (int)lds8(list + (valid ? ci : 0));
           const float4* er = reinterpret_cast<const float4*>(codebook + (long long)c * ED);
           float dot = 0.f;
 #pragma unroll
@@ -385,18 +422,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
           dot += __shfl_xor_sync(0xffffffffu, dot, 1);
           dot += __shfl_xor_sync(0xffffffffu, dot, 2);
           dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-          float dd = __fsub_rn(__fadd_rn(z2, e2s[c]), __fmul_rn(2.f, dot));       // the expression of M.py:64
+          float dd = __fsub_rn(__fadd_rn(z2, lds32f(e2s_u + (uint32_t)c * 4)), __fmul_rn(2.f, dot));   // the expression of M.py:64
           int cc = c;
           if (!valid) { dd = INFINITY; cc = NC; }
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {                                     // combine the four groups
-            const float od = __shfl_xor_sync(0xffffffffu, dd, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, cc, o);
-            if (od < dd || (od == dd && oc < cc)) { dd = od; cc = oc; }
-          }
+          const float od = __shfl_xor_sync(0xffffffffu, dd, 8);            // the other candidate of this row
+          const int oc = __shfl_xor_sync(0xffffffffu, cc, 8);
+          if (od < dd || (od == dd && oc < cc)) { dd = od; cc = oc; }
           if (dd < best || (dd == best && cc < bk)) { best = dd; bk = cc; }
         }
-        if (lane == src && bk < NC) k1 = bk;      // all-NaN rows keep the screen's answer (0, like torch.argmin)
+        const int ra = __shfl_sync(0xffffffffu, bk, 0), rb = __shfl_sync(0xffffffffu, bk, 16);
+        if (lane == sa && ra < NC) k1 = ra;       // all-NaN rows keep the screen's answer (0, like torch.argmin)
+        if (lane == sb && rb < NC) k1 = rb;
       }
       if (g < rows) index[g] = (long long)k1;
       if (warp == MMA_WARP + 1) VQ_ADD(9, t_e3);
@@ -421,8 +457,8 @@ extern "C" int pm_l2_argmin_tc(const float* z, long long rows, int rows_per_batc
                                const float* codebook, const float* e2,
                                int n_codes, int e_dim, long long* index, int max_ctas, void* stream) {
   PM_REQUIRE(z && codebook && e2 && index && rows >= 0);
-  if (rows_per_batch <= 0) { rows_per_batch = 0x7fffffff; z_bs = 0; }      // one dense (rows, 256) matrix
-  PM_REQUIRE((z_bs & 3) == 0);
+  if (rows_per_batch <= 0 || z_bs == (long long)rows_per_batch * ED) { rows_per_batch = 0; z_bs = 0; }   // one dense (rows, 256) matrix
+  PM_REQUIRE((z_bs & 3) == 0 && (rows_per_batch == 0 || rows < 0x7fffffffLL));
   if (e_dim != ED || n_codes != NC) return PM_EUNSUPPORTED;
   PM_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0);
   if (rows == 0) return PM_OK;
