@@ -8,13 +8,12 @@
 // error are re-scored in exact fp32 (same expression and tie rule as the SIMT kernel).  The emitted index is
 // therefore the fp32 argmin for every row, while each row's 1 KB is read from HBM once.
 //
-// Persistent kernel, one CTA per SM, 544 threads:
+// Persistent kernel, one CTA per SM, 416 threads:
 //   warps 0-7   loaders    - coalesced float4 loads of 8 full rows per warp and batch (16 x 16 B in flight per thread),
 //                            per-row max / sum of squares by warp shuffle, power-of-two row scaling into the fp16
 //                            range, fp16 conversion into the 128B-swizzled K-major UMMA layout
 //   warp  8     MMA issuer - 16 x tcgen05.mma (M=128, N=256, K=16) per tile into one of two TMEM accumulators
-//   warps 9-16  epilogue   - two groups of four warps taking alternate tiles (group = TMEM accumulator), each:
-//                            tcgen05.ld, screened distances d~ = e2[k] - 2 z.e (row scale folded into the FMA),
+//   warps 9-12  epilogue   - tcgen05.ld, screened distances d~ = e2[k] - 2 z.e (row scale folded into the FMA),
 //                            pass 1: minimum, pass 2: every k within tau of it; rows with more than one candidate
 //                            are re-scored in fp32 by the whole warp (8 lanes per candidate, shuffle reduction)
 // The fp16 codebook (128 KB, scaled by a power of two) stays resident in shared memory for the CTA's lifetime.
@@ -32,7 +31,10 @@ namespace {
 constexpr int ED = 256;                 // e_dim
 constexpr int NC = 256;                 // codes
 constexpr int TM = 128;                 // rows per tile (UMMA M)
-constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 8;      // epilogue = warps 9..16: two groups of four, one per TMEM accumulator
+constexpr int EPI_GROUPS = 1;           // epilogue warp groups of four taking alternate tiles.  Measured (profiles/r2/vq_*):
+                                        // with the lean passes one group is far from the bottleneck, and a second one
+                                        // (17 warps) caps the kernel at 96 registers per thread, which slows the loaders
+constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 4 * EPI_GROUPS;      // epilogue = warps 9..
 constexpr int NTHREADS = 32 * (LOAD_WARPS + 1 + EPI_WARPS);     // 416
 constexpr int KB_A = TM * 128;          // bytes of one 64-channel k-block of the z tile (16 KB)
 constexpr int KB_B = NC * 128;          // ... of the codebook (32 KB)
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
   if (tid == 0) {
     mbar_init(a_full, LOAD_WARPS);
     mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, EPI_WARPS / 2); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, 4); }
     for (int s = 0; s < SLOTS; ++s) mbar_init(info_full + 8 * s, LOAD_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,63 +180,106 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     // ===== loaders =====
     const float bound_c = 2.0f * 0.0009765625f * 1.02f * emax;        // B = bound_c * |z|  (2 * 2^-10 * 1.02 * |e|max)
     const float inv_cb = pow2i(-s_cb);
+    // Instruction budget matters as much as bytes in flight here (ncu, profiles/r2/ncu_vq_*.md: the first version
+    // issued 37 000 warp-instructions per tile, 23 000 of them in this loop, and the SM was issue-bound at 44 % of HBM):
+    //  - one row statistic only, sum of squares: the scale comes from |z| (>= every |z_d|), reduced by a halving
+    //    butterfly (9 shuffles for 8 rows instead of 80) that leaves row j's total on lanes 4j..4j+3;
+    //  - the owner lanes compute scale / multiplier / tau once, the scale is broadcast back with one shuffle per row;
+    //  - dense full tiles address their rows with immediates off one base pointer;
+    //  - the NEXT batch's 8 KB are pulled into L2 by one bulk prefetch while this batch is reduced and converted, so
+    //    HBM stays busy during the convert phase and the demand loads hit L2.
+    const bool dense = rows_per_batch == 0;
+    auto batch_base = [&](long long tl, int half) { return z + (tl * TM + warp * 16 + half * 8) * ED; };
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const long long r0 = tile * TM;
       const int slot = it & (SLOTS - 1);
+      const bool full = dense && r0 + TM <= rows;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int rb = warp * 16 + half * 8;
         VQ_T(t_ld);
+        if (lane == 0) {                                   // L2 prefetch of this warp's next batch (8 rows = 8 KB)
+          const long long nt = half == 0 ? tile : tile + gridDim.x;
+          if (dense && nt * TM + TM <= rows)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(batch_base(nt, half ^ 1)), "r"(8 * ED * 4) : "memory");
+        }
         float4 v[8][2];
+        if (full) {
+          const float4* p = reinterpret_cast<const float4*>(batch_base(tile, half)) + lane;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long g = r0 + rb + j;
-          if (g < rows) {
-            const float4* p = reinterpret_cast<const float4*>(row_ptr(g));
-            v[j][0] = ldg_stream4(p + lane);
-            v[j][1] = ldg_stream4(p + 32 + lane);
-          } else {
-            v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 8; ++j) {
+            v[j][0] = ldg_stream4(p + j * (ED / 4));
+            v[j][1] = ldg_stream4(p + j * (ED / 4) + 32);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long g = r0 + rb + j;
+            if (g < rows) {
+              const float4* p = reinterpret_cast<const float4*>(row_ptr(g));
+              v[j][0] = ldg_stream4(p + lane);
+              v[j][1] = ldg_stream4(p + 32 + lane);
+            } else {
+              v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
-        float ss[8], mx[8];
+        float ss[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 a = v[j][0], b = v[j][1];
           ss[j] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, fmaf(b.x, b.x, fmaf(b.y, b.y, fmaf(b.z, b.z, b.w * b.w)))))));
-          mx[j] = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
-                        fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
         }
+        // halving butterfly: after the xor-16 / 8 / 4 steps each lane holds ONE row's partial, then two full steps
+        {
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+          for (int i = 0; i < 4; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, h16 ? ss[i] : ss[i + 4], 16);
+            ss[i] = (h16 ? ss[i + 4] : ss[i]) + recv;
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
-            mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+          for (int i = 0; i < 2; ++i) {
+            const float recv = __shfl_xor_sync(0xffffffffu, h8 ? ss[i] : ss[i + 2], 8);
+            ss[i] = (h8 ? ss[i + 2] : ss[i]) + recv;
+          }
+          const float recv = __shfl_xor_sync(0xffffffffu, h4 ? ss[0] : ss[1], 4);
+          ss[0] = (h4 ? ss[1] : ss[0]) + recv;
+          ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 2);
+          ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 1);
+        }
+        // this lane owns row (lane >> 2) & 7 of the batch: |z| < 2^(floor(e/2)+1) for |z|^2 = m 2^e, so scaling by
+        // 2^(13 - floor(e/2)) keeps every element below 2^14 (no fp16 overflow whatever the data's scale)
+        const float ss_own = ss[0];
+        int s_own = 0;
+        {
+          const int ex = (int)(__float_as_uint(ss_own) >> 23) & 0xFF;
+          if (ex != 0 && ex != 255) {
+            s_own = 13 - ((ex - 127) >> 1);
+            s_own = s_own < -100 ? -100 : (s_own > 100 ? 100 : s_own);
           }
         }
+        const float sc_own = pow2i(s_own);
         if (warp == 0) VQ_ADD(0, t_ld);
         VQ_T(t_we);
         if (half == 0) mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);  // previous tile's MMAs have read the A tile
         if (warp == 0) VQ_ADD(1, t_we);
         VQ_T(t_cv);
+        if ((lane & 3) == 0) {
+          // d~ = e2[k] + mult * acc ;  tau = 2 B + fp32 slack (covers the exact path's own rounding and flushes)
+          const float mult = -2.0f * pow2i(-s_own) * inv_cb;
+          const float tau = 2.0f * bound_c * sqrtf(ss_own) + 2.4e-7f * 16.f * (ss_own + e2max);
+          sts64(info_u + (uint32_t)(slot * TM + rb + (lane >> 2)) * 8, __float_as_uint(mult), __float_as_uint(tau));
+        }
+        // lane holds channels 4*lane..+3 (k-block lane/16) and 128 + 4*lane..+3 (k-block 2 + lane/16)
+        const uint32_t dst0 = sm_u + Smem::A + (lane >> 4) * KB_A + (uint32_t)((rb >> 3) * 1024);   // rb is a multiple of 8
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rb + j;
-          const int s = scale_exp(mx[j]);
-          const float sc = pow2i(s);
-          // lane holds channels 4*lane..+3 (k-block lane/16) and 128 + 4*lane..+3 (k-block 2 + lane/16)
-          const int byte = (lane & 15) * 8;
-          const uint32_t dst = sm_u + Smem::A + (lane >> 4) * KB_A + sw128(r, byte);
+        for (int j = 0; j < 8; ++j) {                      // row rb + j: 8-row group rb / 8, row j within it
+          const float sc = __shfl_sync(0xffffffffu, sc_own, 4 * j);
+          const uint32_t dst = dst0 + (uint32_t)(j * 128 + ((((lane & 15) >> 1) ^ j) << 4) + (lane & 1) * 8);
           sts64(dst, pack_h2(v[j][0].x * sc, v[j][0].y * sc), pack_h2(v[j][0].z * sc, v[j][0].w * sc));
           sts64(dst + 2 * KB_A, pack_h2(v[j][1].x * sc, v[j][1].y * sc), pack_h2(v[j][1].z * sc, v[j][1].w * sc));
-          if (lane == j) {
-            // d~ = e2[k] + mult * acc ;  tau = 2 B + fp32 slack (covers the exact path's own rounding and flushes)
-            const float mult = -2.0f * pow2i(-s) * inv_cb;
-            const float tau = 2.0f * bound_c * sqrtf(ss[j]) + 2.4e-7f * 16.f * (ss[j] + e2max);
-            sts64(info_u + (uint32_t)(slot * TM + r) * 8, __float_as_uint(mult), __float_as_uint(tau));
-          }
         }
         if (warp == 0) VQ_ADD(2, t_cv);
       }
@@ -274,14 +319,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     }
   } else {
     // ===== epilogue: TMEM lane quarter = warp % 4, thread = one row of the tile =====
-    // The epilogue is the longest stage of the pipeline (two passes over 256 columns + re-scoring), so two groups of
-    // four warps take alternate tiles: group = TMEM accumulator buffer, no communication between the groups.
+    // EPI_GROUPS groups of four warps take alternate tiles (no communication between groups).
     const int q = warp & 3;
-    const int grp = (warp - (MMA_WARP + 1)) >> 2;
+    const int grp = (warp - (MMA_WARP + 1)) >> 2;            // 0 .. EPI_GROUPS-1
     const int trow = q * 32 + lane;
     const uint32_t cands_g = cands_u + (uint32_t)(grp * TM * MAXC);
     int it = grp;
-    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < n_tiles; tile += 2LL * gridDim.x, it += 2) {
+    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < n_tiles; tile += (long long)EPI_GROUPS * gridDim.x, it += EPI_GROUPS) {
       const int buf = it & 1, slot = it & (SLOTS - 1);
       const long long g = tile * TM + trow;
       VQ_T(t_e0);
