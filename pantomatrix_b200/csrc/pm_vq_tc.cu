@@ -31,7 +31,10 @@ namespace {
 constexpr int ED = 256;                 // e_dim
 constexpr int NC = 256;                 // codes
 constexpr int TM = 128;                 // rows per tile (UMMA M)
-constexpr int EPI_GROUPS = 1;           // epilogue warp groups of four taking alternate tiles.  Measured (profiles/r2/vq_*):
+#ifndef PM_VQ_EPI_GROUPS
+#define PM_VQ_EPI_GROUPS 2
+#endif
+constexpr int EPI_GROUPS = PM_VQ_EPI_GROUPS;           // epilogue warp groups of four taking alternate tiles.  Measured (profiles/r2/vq_*):
                                         // with the lean passes one group is far from the bottleneck, and a second one
                                         // (17 warps) caps the kernel at 96 registers per thread, which slows the loaders
 constexpr int LOAD_WARPS = 8, MMA_WARP = 8, EPI_WARPS = 4 * EPI_GROUPS;      // epilogue = warps 9..
@@ -66,7 +69,7 @@ struct Smem {
   static constexpr int INFO = E2 + NC * 4;                  // float2[SLOTS][TM]: (fma multiplier, tau)
   static constexpr int CAND = INFO + SLOTS * TM * 8;        // uint8[2 groups][TM][MAXC]
   static constexpr int BARS = CAND + 2 * TM * MAXC;         // mbarriers
-  static constexpr int N_BARS = 2 + 2 + 2 + SLOTS;          // a_full, a_empty, acc_full[2], acc_empty[2], info_full[SLOTS]
+  static constexpr int N_BARS = 2 + 2 + 2 + SLOTS + 1;      // a_full, a_empty (k-blocks 0-1), acc_full[2], acc_empty[2], info_full[SLOTS], a_empty_hi (k-blocks 2-3)
   static constexpr int MISC = BARS + N_BARS * 8;            // tmem slot, emax
   static constexpr int TOTAL = MISC + 16;
 };
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
   // every hot access below is an explicit ld/st.shared (generic pointers cost a 64-bit address computation each)
   const uint32_t bars = sm_u + Smem::BARS;
   const uint32_t a_full = bars, a_empty = bars + 8, acc_full = bars + 16, acc_empty = bars + 32, info_full = bars + 48;
+  const uint32_t a_empty_hi = info_full + 8 * SLOTS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::MISC);
   float* misc_f = reinterpret_cast<float*>(sm + Smem::MISC + 4);       // [0] = max |e_k|^2
 
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
   if (tid == 0) {
     mbar_init(a_full, LOAD_WARPS);
     mbar_init(a_empty, 1);
+    mbar_init(a_empty_hi, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full + 8 * b, 1); mbar_init(acc_empty + 8 * b, 4); }
     for (int s = 0; s < SLOTS; ++s) mbar_init(info_full + 8 * s, LOAD_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -186,8 +191,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     //    butterfly (9 shuffles for 8 rows instead of 80) that leaves row j's total on lanes 4j..4j+3;
     //  - the owner lanes compute scale / multiplier / tau once, the scale is broadcast back with one shuffle per row;
     //  - dense full tiles address their rows with immediates off one base pointer;
-    //  - the NEXT batch's 8 KB are pulled into L2 by one bulk prefetch while this batch is reduced and converted, so
-    //    HBM stays busy during the convert phase and the demand loads hit L2.
+    //  - the warp's 16 KB of the NEXT tile are pulled into L2 by one bulk prefetch a whole tile period ahead, so HBM
+    //    stays busy during the convert phases and the demand loads hit L2 (a software-pipelined variant with four
+    //    4-row quads through two register sets was measured slower: 44 % against 55 %, profiles/r2/vq_history.md).
     const bool dense = rows_per_batch == 0;
     auto batch_base = [&](long long tl, int half) { return z + (tl * TM + warp * 16 + half * 8) * ED; };
     int it = 0;
@@ -199,10 +205,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       for (int half = 0; half < 2; ++half) {
         const int rb = warp * 16 + half * 8;
         VQ_T(t_ld);
-        if (lane == 0) {                                   // L2 prefetch of this warp's next batch (8 rows = 8 KB)
-          const long long nt = half == 0 ? tile : tile + gridDim.x;
+        if (lane == 0 && half == 0) {                      // L2 prefetch one whole tile ahead: this warp's 16 rows (16 KB)
+          const long long nt = tile + gridDim.x;
           if (dense && nt * TM + TM <= rows)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(batch_base(nt, half ^ 1)), "r"(8 * ED * 4) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(batch_base(nt, 0)), "r"(16 * ED * 4) : "memory");
         }
         float4 v[8][2];
         if (full) {
@@ -263,7 +269,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         const float sc_own = pow2i(s_own);
         if (warp == 0) VQ_ADD(0, t_ld);
         VQ_T(t_we);
-        if (half == 0) mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);  // previous tile's MMAs have read the A tile
+        // The previous tile's MMAs must have read the A tile before it is overwritten.  They release it in two halves
+        // (k-blocks 0-1, then 2-3), so the first halves of this batch's rows are stored while the MMAs of k-blocks 2-3
+        // still run.
+        if (half == 0) mbar_wait_relaxed(a_empty, (uint32_t)(it & 1) ^ 1u);
         if (warp == 0) VQ_ADD(1, t_we);
         VQ_T(t_cv);
         if ((lane & 3) == 0) {
@@ -275,11 +284,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         // lane holds channels 4*lane..+3 (k-block lane/16) and 128 + 4*lane..+3 (k-block 2 + lane/16)
         const uint32_t dst0 = sm_u + Smem::A + (lane >> 4) * KB_A + (uint32_t)((rb >> 3) * 1024);   // rb is a multiple of 8
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                      // row rb + j: 8-row group rb / 8, row j within it
+        for (int j = 0; j < 8; ++j) {                      // row rb + j: 8-row group rb / 8, row j within it; k-blocks 0 / 1
           const float sc = __shfl_sync(0xffffffffu, sc_own, 4 * j);
           const uint32_t dst = dst0 + (uint32_t)(j * 128 + ((((lane & 15) >> 1) ^ j) << 4) + (lane & 1) * 8);
           sts64(dst, pack_h2(v[j][0].x * sc, v[j][0].y * sc), pack_h2(v[j][0].z * sc, v[j][0].w * sc));
-          sts64(dst + 2 * KB_A, pack_h2(v[j][1].x * sc, v[j][1].y * sc), pack_h2(v[j][1].z * sc, v[j][1].w * sc));
+        }
+        if (half == 0) mbar_wait_relaxed(a_empty_hi, (uint32_t)(it & 1) ^ 1u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                      // k-blocks 2 / 3
+          const float sc = __shfl_sync(0xffffffffu, sc_own, 4 * j);
+          const uint32_t dst = dst0 + (uint32_t)(j * 128 + ((((lane & 15) >> 1) ^ j) << 4) + (lane & 1) * 8) + 2 * KB_A;
+          sts64(dst, pack_h2(v[j][1].x * sc, v[j][1].y * sc), pack_h2(v[j][1].z * sc, v[j][1].w * sc));
         }
         if (warp == 0) VQ_ADD(2, t_cv);
       }
@@ -297,22 +312,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       VQ_T(t_m0);
-      mbar_wait(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
+      mbar_wait_relaxed(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
       VQ_ADD(3, t_m0);
       VQ_T(t_m1);
-      mbar_wait(a_full, (uint32_t)(it & 1));
+      mbar_wait_relaxed(a_full, (uint32_t)(it & 1));
       VQ_ADD(4, t_m1);
       VQ_CNT(11, 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)buf * NC;
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
+        for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_bf16(d, a_desc + (uint64_t)(kb * (KB_A >> 4) + k * 2), b_desc + (uint64_t)(kb * (KB_B >> 4) + k * 2), IDESC,
                         (uint32_t)((kb | k) != 0));
-        tc_commit(a_empty);
+          if (kb == 1) tc_commit(a_empty);                 // k-blocks 0-1 of the A tile may be overwritten
+        }
+        tc_commit(a_empty_hi);
         tc_commit(acc_full + 8 * buf);
       }
       __syncwarp();
@@ -329,9 +346,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       const int buf = it & 1, slot = it & (SLOTS - 1);
       const long long g = tile * TM + trow;
       VQ_T(t_e0);
-      mbar_wait(info_full + 8 * slot, (uint32_t)((it >> 2) & 1));
+      mbar_wait_relaxed(info_full + 8 * slot, (uint32_t)((it >> 2) & 1));
       const float2 inf = lds64f(info_u + (uint32_t)(slot * TM + trow) * 8);
-      mbar_wait(acc_full + 8 * buf, (uint32_t)((it >> 1) & 1));
+      mbar_wait_relaxed(acc_full + 8 * buf, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (warp == MMA_WARP + 1) VQ_ADD(6, t_e0);
       VQ_T(t_e1);
@@ -340,10 +357,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       // of 256 dependent compare-selects was latency bound) and the next TMEM chunk in flight while this one is reduced.
       float mm[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
       int kk[4] = {0, 1, 2, 3};
-      uint32_t accA[32], accB[32];
-      auto reduce_chunk = [&](const uint32_t (&acc)[32], int c0) {
+      uint32_t accA[16], accB[16];             // 16-column chunks: two in flight cost 32 registers (the kernel is capped at 96)
+      auto reduce_chunk = [&](const uint32_t (&acc)[16], int c0) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < 4; ++j4) {
           const float4 e = lds128(e2s_u + (uint32_t)(c0 + 4 * j4) * 4);
           const float d0 = fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x), d1 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y);
           const float d2 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z), d3 = fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w);
@@ -353,15 +370,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
           if (d3 < mm[3]) { mm[3] = d3; kk[3] = c0 + 4 * j4 + 3; }
         }
       };
-      tmem_ld32_issue(taddr, accA);
+      tmem_ld16_issue(taddr, accA);
 #pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 64) {
-        tmem_ld32_wait(accA);
-        tmem_ld32_issue(taddr + c0 + 32, accB);
+      for (int c0 = 0; c0 < NC; c0 += 32) {
+        tmem_ld16_wait(accA);
+        tmem_ld16_issue(taddr + c0 + 16, accB);
         reduce_chunk(accA, c0);
-        tmem_ld32_wait(accB);
-        tmem_ld32_issue(taddr + ((c0 + 64) & (NC - 1)), accA);       // wraps to chunk 0: the first chunk of pass 2
-        reduce_chunk(accB, c0 + 32);
+        tmem_ld16_wait(accB);
+        tmem_ld16_issue(taddr + ((c0 + 32) & (NC - 1)), accA);       // wraps to chunk 0: the first chunk of pass 2
+        reduce_chunk(accB, c0 + 16);
       }
       float m1 = mm[0];
       int k1 = kk[0];
@@ -372,38 +389,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       VQ_T(t_e2);
       // pass 2: every code within tau of the minimum (the minimum itself included: nc >= 1)
       const float thr = m1 + inf.y;
-      int nc = 0;
       const uint32_t my = cands_g + (uint32_t)(trow * MAXC);
-      // The fully unrolled body stays tiny and branch-free: FFMA + compare + one predicated bit-set per code.  The
-      // (rare) hits of a 32-code chunk are then appended to the row's list by a short rolled loop.  Anything bigger
-      // inline makes the pass instruction-fetch / issue bound (13 000 instead of ~1 500 cycles per tile, measured).
-      auto collect_chunk = [&](const uint32_t (&acc)[32], int c0) {
-        uint32_t hits = 0;
+      // The fully unrolled body stays tiny and branch-free: FFMA + compare + one predicated bit-set per code, one hit
+      // mask per 32 codes.  Anything bigger inline - candidate bookkeeping, even a short extraction loop per
+      // chunk - makes the pass issue / fetch bound (13 000 -> 3 700 -> ~1 500 cycles per tile, profiles/r2/vq_timeline_*).
+      uint32_t hits[8];
+      auto mask_chunk = [&](const uint32_t (&acc)[16], int c0, int bit0) {
+        uint32_t h = 0;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < 4; ++j4) {
           const float4 e = lds128(e2s_u + (uint32_t)(c0 + 4 * j4) * 4);
-          if (fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x) <= thr) hits |= 1u << (4 * j4);
-          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y) <= thr) hits |= 1u << (4 * j4 + 1);
-          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z) <= thr) hits |= 1u << (4 * j4 + 2);
-          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w) <= thr) hits |= 1u << (4 * j4 + 3);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4]), e.x) <= thr) h |= 1u << (bit0 + 4 * j4);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 1]), e.y) <= thr) h |= 1u << (bit0 + 4 * j4 + 1);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 2]), e.z) <= thr) h |= 1u << (bit0 + 4 * j4 + 2);
+          if (fmaf(inf.x, __uint_as_float(acc[4 * j4 + 3]), e.w) <= thr) h |= 1u << (bit0 + 4 * j4 + 3);
         }
-#pragma unroll 1
-        while (hits) {
-          const int j = __ffs(hits) - 1;
-          hits &= hits - 1;
-          sts8(my + (uint32_t)(nc & (MAXC - 1)), (uint32_t)(c0 + j));
-          ++nc;
-        }
+        return h;
       };
-#pragma unroll 1
-      for (int c0 = 0; c0 < NC; c0 += 64) {
-        tmem_ld32_wait(accA);
-        tmem_ld32_issue(taddr + c0 + 32, accB);
-        collect_chunk(accA, c0);
-        tmem_ld32_wait(accB);
-        if (c0 + 64 < NC) tmem_ld32_issue(taddr + c0 + 64, accA);
-        collect_chunk(accB, c0 + 32);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld16_wait(accA);
+        tmem_ld16_issue(taddr + 32 * c + 16, accB);
+        hits[c] = mask_chunk(accA, 32 * c, 0);
+        tmem_ld16_wait(accB);
+        if (c < 7) tmem_ld16_issue(taddr + 32 * c + 32, accA);
+        hits[c] |= mask_chunk(accB, 32 * c + 16, 16);
       }
+      int nc = 0;                                          // codes within tau of the minimum (the minimum included)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) nc += __popc(hits[c]);
       if (warp == MMA_WARP + 1) VQ_ADD(8, t_e2);
       VQ_T(t_e3);
       // accumulator drained: hand it back to the MMA warp before the (rare, slow) exact re-scoring
@@ -411,11 +425,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
       const bool flagged = nc > 1 && g < rows;            // more than one code within the screen's error bound
-      if (flagged && nc <= MAXC) {                        // pull the operands of the re-scoring into L1 meanwhile
+      if (flagged && nc <= MAXC) {                        // ~5 % of the rows: list the candidates, pull their operands into L1
         prefetch_row(row_ptr(g));
-#pragma unroll 1
-        for (int i = 0; i < nc; ++i) prefetch_row(codebook + (long long)lds8(my + i) * ED);
+        int n = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t h = hits[c];
+          while (h) {
+            const int k = 32 * c + __ffs(h) - 1;
+            h &= h - 1;
+            sts8(my + (uint32_t)n, (uint32_t)k);
+            ++n;
+            prefetch_row(codebook + (long long)k * ED);
+          }
+        }
       }
+      __syncwarp();
 
       // ---- exact fp32 re-scoring of rows with more than one candidate.  Two rows per round (one per half warp: the
       // loop is a chain of memory round trips, so two independent chains run for the price of one), two candidates at
