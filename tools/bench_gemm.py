@@ -1,5 +1,5 @@
 """Microbenchmark of pm_tapgemm_tc on the EMAGE shapes (warm L2, CUDA events around CUDA-graph replays).
-    [PM_TC_BN=64|128] [PM_TC_SMEM_KB=...] python tools/bench_gemm.py"""
+    python tools/bench_gemm.py [shape-substring] [fp16]      # fp16: two fp16 planes (the default engine) only"""
 import math
 import os
 import sys
@@ -30,7 +30,10 @@ SHAPES = [  # name, batch, rows, cin, cout, taps, pad
 
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
-    print(f"PM_TC_BN={os.environ.get('PM_TC_BN', 'auto')} PM_TC_SMEM_KB={os.environ.get('PM_TC_SMEM_KB', '200')}")
+    fp16 = len(sys.argv) > 2 and sys.argv[2] == "fp16"
+    if fp16:
+        ops.set_plane_format("fp16")
+    print(f"plane format {ops.plane_format()}")
     print(f"{'shape':34s} {'ns':>2s} {'out':>4s} {'us':>9s} {'TFLOP/s(alg)':>13s} {'bf16-equiv':>10s}")
     for name, b, rows, cin, cout, taps, pad in SHAPES:
         if only and only not in name:
@@ -40,7 +43,7 @@ def main():
         w = (torch.randn(taps, cout, cin, generator=g) / math.sqrt(cin * taps)).cuda()
         bias = torch.zeros(cout, device="cuda")
         rows_out = rows + 2 * pad - taps + 1
-        for ns in (1, 2, 3):
+        for ns in ((2,) if fp16 else (1, 2, 3)):
             a = ops.split_bf16(x, ns)
             pw = ops.PackedW(w, ns)
             for out_mode in ("f32", "f+p"):
@@ -64,7 +67,7 @@ def main():
                 torch.cuda.synchronize()
                 us = s.elapsed_time(e) / 60 * 1e3
                 fl = 2.0 * b * rows_out * cout * cin * taps
-                mult = {1: 1, 2: 3, 3: 6}[ns]
+                mult = {1: 1, 2: 3, 3: 6}[ns]          # tensor-core products per fp32 product
                 print(f"{name:34s} {ns:2d} {out_mode:>4s} {us:9.1f} {fl / us / 1e6:13.1f} {fl * mult / us / 1e6:10.1f}")
 
 
