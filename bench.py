@@ -45,7 +45,8 @@ ENGINES = {"fp32": "fp32 SIMT tap-GEMM", "fp16x3": "tcgen05 tap-GEMM, 3 fp16 pro
 MMA_PER_PRODUCT = {"fp32": 0, "bf16": 1, "bf16x3": 3, "bf16x6": 6, "fp16x3": 3}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch from a committed `ncu --set full` capture
 # (a static number, not measured in this run): precision -> (bytes, source file under profiles/)
-NCU_TRAFFIC = {"bf16x6": (26.4e6, "profiles/ncu_full_r1_final.md")}
+NCU_TRAFFIC = {"bf16x6": (26.4e6, "profiles/ncu_full_r1_final.md"),
+               "fp16x3": (8.711e6, "profiles/r2/ncu_full.md (8.711 MB read + 0 B written; algorithmic operand bytes 8.65 MB)")}
 METRIC = "motion_frames_per_sec"
 UNIT = "frames/s"
 
