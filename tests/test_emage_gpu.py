@@ -57,6 +57,10 @@ def _pose_checks(pred, want_aa, want_expr, want_trans, tag, frames=None, raw=Non
         allowed = torch.maximum(allowed, 1e-4 * kappa)
         assert (kappa > 10).double().mean() < 0.03, (tag, "too many ill-conditioned joints to be a meaningful gate")
     bad = (geo > allowed) & keep[:, :, None]
+    used = geo[keep[:, :, None].expand_as(geo)] / allowed[keep[:, :, None].expand_as(geo)]
+    print(f"[{tag}] pose gate: max geodesic error {geo[keep[:, :, None].expand_as(geo)].max().item():.2e} rad, "
+          f"largest fraction of the allowed bound used {used.max().item():.3f}"
+          + (f", joints under the conditioning-aware bound (kappa > 10): {(allowed > 1e-3).double().mean().item():.4f}" if raw is not None else ""))
     assert not bad.any(), (tag, "geodesic rad", geo[bad].max().item(), int(bad.sum()))
     # component-wise check away from the axis-angle discontinuity at pi (|aa| error <= ~1.5 x geodesic there)
     far = ((want_aa.reshape(bs, T, 55, 3).norm(dim=-1) < 2.0) & (allowed <= 1e-3)).repeat_interleave(3, dim=-1) & keep[:, :, None]
@@ -82,6 +86,7 @@ def _face_ties(vqm, vq, lat, want_lat, tag, max_ties=0):
         gap = (d.gather(1, got[diff][:, None]) - d.gather(1, want[diff][:, None])).abs()[:, 0]
         rel = gap / d.min(1).values.abs()
         assert bool((rel < 2e-5).all()), (tag, "face index differs on a decidable row", rel.max().item())
+    print(f"\n[{tag}] face codes differing from the oracle: {int(diff.sum())} of {diff.numel()} (allowed: {max_ties} proven fp64 ties)")
     assert int(diff.sum()) <= max_ties, (tag, f"{int(diff.sum())} undecidable face ties")
     # a code feeds a k=3 conv decoder with a +-9 frame receptive field: exclude the neighbourhood too
     near = torch.nn.functional.max_pool1d(diff.float().unsqueeze(1), 19, 1, 9)[:, 0] > 0
