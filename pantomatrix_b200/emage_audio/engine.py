@@ -85,6 +85,34 @@ def _pk(nsplit: int) -> int:
     return nsplit | (ops.FMT_F16 if ops.plane_format() == "fp16" else 0)
 
 
+def guarded(run, checked):
+    """Run `run()` in the current precision; in the fp16x3 engine verify afterwards that no GEMM operand left the
+    fp16 range and, if one did, recompute in bf16x6 (same accuracy, fp32 exponent range) - still on the GPU, with a
+    warning.  `checked(result)` returns the fp32 tensors whose NaN would reveal the overflow (an out-of-range operand
+    becomes inf - inf = NaN in the consuming GEMM and propagates to every output).  Inside a CUDA-graph capture nothing
+    can be read back: the captured pipeline carries the flag itself (pipeline.CapturedPipeline)."""
+    out = run()
+    if ops.plane_format() != "fp16":
+        return out
+    tensors = [t for t in checked(out) if t is not None]
+    if not tensors or not tensors[0].is_cuda or torch.cuda.is_current_stream_capturing():
+        return out
+    flag = ops.zero_flag(tensors[0].device)
+    for t in tensors:
+        ops.row_argmax(t, nonfinite=flag)                # the kernel that reads the logits anyway; indices discarded
+    if not bool(flag):
+        return out
+    import warnings
+    warnings.warn("fp16x3: a GEMM operand exceeded the fp16 range (|x| > 1023 after the x64 pre-scale); "
+                  "recomputing this call with engine.set_precision('bf16x6') - select it up front for this checkpoint")
+    prev = get_precision()
+    set_precision("bf16x6")
+    try:
+        return run()
+    finally:
+        set_precision(prev)
+
+
 def _record_stream(obj, stream):
     if isinstance(obj, torch.Tensor):
         if obj.is_cuda:

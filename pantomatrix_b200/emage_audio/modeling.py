@@ -394,12 +394,15 @@ class EmageAudioModel(_EngineOwner):
         mask = mask.to(device=dev, dtype=torch.float32).contiguous()
         bs, t, ch = motion.shape
         # no seed splice here: pre = 0 makes window_input the plain `where(mask==1, embedding, motion)`
-        ns = E._ns()
-        win_in = ops.window_input(motion, mask, None, eng.mask_embedding, 0, t, 0,
-                                  nsplit=ns, f32=ns == 0)
-        mem_face, kv = eng.audio_phase(audio, 0, 0, 1, audio.shape[1], t)
-        return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv)
+
+        def run():
+            ns = E._ns()
+            win_in = ops.window_input(motion, mask, None, eng.mask_embedding, 0, t, 0, nsplit=ns, f32=ns == 0)
+            mem_face, kv = eng.audio_phase(audio, 0, 0, 1, audio.shape[1], t)
+            return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv)
+        return E.guarded(run, lambda out: [out["cls_" + p] for p in E.PARTS])
 
     def inference(self, audio, speaker_id, vq_model, masked_motion=None, mask=None):
         """Sliding-window generation (M.py:343-490)."""
-        return E.run_inference(self._eng(), vq_model.engine(), audio, speaker_id, masked_motion, mask)
+        return E.guarded(lambda: E.run_inference(self._eng(), vq_model.engine(), audio, speaker_id, masked_motion, mask),
+                         lambda out: [out["cls_" + p] for p in E.PARTS])

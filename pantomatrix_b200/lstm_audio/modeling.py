@@ -167,7 +167,9 @@ class _LstmModelBase(_EngineOwner):
 
     def forward(self, audio, speaker_id, seed_frames=4, seed_motion=None, return_axis_angle=True):
         """audio (bs, n) 16 kHz, speaker_id (bs, 1) long, optional seed_motion (bs, t_m, pose_dims) rot6d."""
-        return self._eng().forward(audio, speaker_id, seed_frames, seed_motion, return_axis_angle)
+        from ..emage_audio import engine as E
+        return E.guarded(lambda: self._eng().forward(audio, speaker_id, seed_frames, seed_motion, return_axis_angle),
+                         lambda out: [out["motion"]])
 
 
 class CamnAudioPreTrainedModel(_LstmModelBase):

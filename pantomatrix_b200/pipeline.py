@@ -9,8 +9,9 @@ import torch
 from . import _lib, ops
 from .emage_audio.engine import PARTS, select_inputs
 
-_OVERFLOW = ("fp16x3: a GEMM operand exceeded the fp16 range (|x| > 65504) and the result is NaN - "
-             "rerun with engine.set_precision('bf16x6')")
+_OVERFLOW = ("fp16x3: a GEMM operand exceeded the fp16 range (|x| > 1023 after the x64 pre-scale) and the result is NaN - "
+             "use engine.set_precision('bf16x6') for this checkpoint (model.inference() outside a captured graph retries "
+             "in bf16x6 by itself)")
 
 
 @torch.no_grad()

@@ -265,6 +265,28 @@ def test_tensor_core_precision_modes(product, ckpt, precision, rec_tol, min_agre
     assert same / total >= min_agree, (precision, same, total)
 
 
+def test_fp16_overflow_is_detected_and_recomputed_in_bf16x6(product):
+    """The default fp16x3 engine needs GEMM inputs below 65504 / 64.  Audio 2e4 times louder than the model's range
+    drives the first tensor-core conv far beyond that: inference() must notice (NaN reaches the logits, the argmax
+    kernels raise the flag), warn, and return what the bf16x6 engine computes - never NaNs or out-of-range codes."""
+    from pantomatrix_b200.emage_audio import engine
+    model, vqm = product
+    audio = (torch.from_numpy(synth_audio(2, 40000, 5)) * 2e4).cuda()
+    spk = torch.zeros(2, 1, dtype=torch.long, device="cuda")
+    engine.set_precision("bf16x6")
+    want = model.inference(audio, spk, vqm)
+    assert all(bool(torch.isfinite(v).all()) for v in want.values())
+    engine.set_precision("fp16x3")
+    try:
+        with pytest.warns(UserWarning, match="bf16x6"):
+            got = model.inference(audio, spk, vqm)
+        assert engine.get_precision() == "fp16x3"                      # the retry does not change the selected mode
+    finally:
+        engine.set_precision("fp32")
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+
+
 def test_tokenisation_matches_reference_golden(product, golden_dir):
     """map2index / map2latent / EmageVQVAEConv.forward on the GPU against the real reference's outputs
     (tests/golden/case_tokenise.npz); the CPU twin is tests/test_host_logic.py."""
