@@ -31,8 +31,8 @@ struct Smem {
   static constexpr int K = Q + 2 * KB * BLK;
   static constexpr int V = K + 2 * KB * BLK;
   static constexpr int P = V + 2 * KB * BLK;           // [2 planes] one block each
-  static constexpr int BARS = P + 2 * BLK;             // qk_full, v_full, s_full, p_full, o_full
-  static constexpr int MISC = BARS + 5 * 8;
+  static constexpr int BARS = P + 2 * BLK;             // qk_full[KB], v_full, s_full, p_full, o_full
+  static constexpr int MISC = BARS + (KB + 4) * 8;
   static constexpr int TOTAL = MISC + 16;
   static constexpr int OUT = 0;                        // fp32 output tile [T][HD] staged over Q | K (dead after S)
 };
@@ -64,13 +64,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sm_u = smem_u32(sm);
   const uint32_t bars = sm_u + Smem::BARS;
-  const uint32_t qk_full = bars, v_full = bars + 8, s_full = bars + 16, p_full = bars + 24, o_full = bars + 32;
+  const uint32_t qk_full = bars, v_full = bars + 8 * KB, s_full = v_full + 8, p_full = v_full + 16, o_full = v_full + 24;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::MISC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
 
   if (threadIdx.x == 0) {
-    mbar_init(qk_full, 1);
+    for (int kb = 0; kb < KB; ++kb) mbar_init(qk_full + 8 * kb, 1);
     mbar_init(v_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
@@ -93,12 +93,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-      mbar_expect_tx(qk_full, 4 * KB * BLK);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int kb = 0; kb < KB; ++kb) {
-          tma_load_4d(sm_u + Smem::Q + (pl * KB + kb) * BLK, &map_q, qk_full, p.qc0 + h * HD + kb * 64, 0, b, pl);
-          tma_load_4d(sm_u + Smem::K + (pl * KB + kb) * BLK, &map_k, qk_full, p.kc0 + h * HD + kb * 64, 0, b, pl);
+      for (int kb = 0; kb < KB; ++kb) {                   // one barrier per 64-column block: the first MMAs start on a third of Q, K
+        mbar_expect_tx(qk_full + 8 * kb, 4 * BLK);
+        for (int pl = 0; pl < 2; ++pl) {
+          tma_load_4d(sm_u + Smem::Q + (pl * KB + kb) * BLK, &map_q, qk_full + 8 * kb, p.qc0 + h * HD + kb * 64, 0, b, pl);
+          tma_load_4d(sm_u + Smem::K + (pl * KB + kb) * BLK, &map_k, qk_full + 8 * kb, p.kc0 + h * HD + kb * 64, 0, b, pl);
         }
+      }
       mbar_expect_tx(v_full, 2 * KB * BLK);
       for (int pl = 0; pl < 2; ++pl)
         for (int nb = 0; nb < KB; ++nb)
@@ -106,28 +107,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     }
     __syncwarp();
     // ---- S = Q K^T : D = f32, A = B = f16, both K-major, N = 64, M = 64
-    mbar_wait(qk_full, 0);
-    tc_fence_after();
-    if (elect_one()) {
+    {
       constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(T >> 3) << 17) | ((uint32_t)(T >> 4) << 24);
       const uint64_t q0 = UMMA_DESC_K_SW128 | (uint64_t)(((sm_u + Smem::Q) >> 4) & 0x3FFFu);
       const uint64_t k0 = UMMA_DESC_K_SW128 | (uint64_t)(((sm_u + Smem::K) >> 4) & 0x3FFFu);
       constexpr uint64_t PL = (uint64_t)(KB * BLK) >> 4, KBS = (uint64_t)BLK >> 4;
-      // cross products first (small), the main product last: operands (A plane, B plane) = (0,1), (1,0), (0,0)
+      // per block: cross products first (small), the main product last: (A plane, B plane) = (0,1), (1,0), (0,0)
       const int pa[3] = {0, 1, 0}, pb[3] = {1, 0, 0};
       uint32_t acc = 0;
 #pragma unroll
-      for (int t = 0; t < 3; ++t)
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(qk_full + 8 * kb, 0);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+          for (int t = 0; t < 3; ++t)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma_bf16(tmem_s, q0 + pa[t] * PL + kb * KBS + k * 2, k0 + pb[t] * PL + kb * KBS + k * 2, IDESC_S, acc);
-            acc = 1;
-          }
-      tc_commit(s_full);
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_bf16(tmem_s, q0 + pa[t] * PL + kb * KBS + k * 2, k0 + pb[t] * PL + kb * KBS + k * 2, IDESC_S, acc);
+              acc = 1;
+            }
+          if (kb == KB - 1) tc_commit(s_full);
+        }
+        __syncwarp();
+      }
     }
-    __syncwarp();
     // ---- O = P V : B = V as stored, (keys x dims) = MN-major: 64-dim groups 8 KB apart (LBO), 8-key groups 1 KB (SBO)
     mbar_wait(v_full, 0);
     mbar_wait(p_full, 0);
