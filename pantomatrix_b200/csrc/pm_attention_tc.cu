@@ -34,9 +34,15 @@ struct Smem {
   static constexpr int BARS = P + 2 * BLK;             // qk_full[KB], v_full, s_full, p_full, o_full
   static constexpr int MISC = BARS + (KB + 4) * 8;
   static constexpr int TOTAL = MISC + 16;
-  static constexpr int OUT = 0;                        // fp32 output tile [T][HD] staged over Q | K (dead after S)
 };
-static_assert(T * HD * 4 <= 4 * KB * BLK, "output staging must fit into the Q | K region");
+
+// Instrumented build only (-DPM_ATTN_TIMING, tools/bench_attention.py --timeline): clock64 stamps of CTA 0's phases.
+#ifdef PM_ATTN_TIMING
+__device__ unsigned long long pm_attn_stamps[16];
+#define AT_STAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) pm_attn_stamps[i] = (unsigned long long)clock64(); } while (0)
+#else
+#define AT_STAMP(i) do {} while (0)
+#endif
 
 struct AttnParams {
   int heads, tq, tk;
@@ -68,6 +74,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Smem::MISC);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  if (warp == 0) AT_STAMP(0);                              // kernel entry
 
   if (threadIdx.x == 0) {
     for (int kb = 0; kb < KB; ++kb) mbar_init(qk_full + 8 * kb, 1);
@@ -86,6 +93,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+  if (warp == 0) AT_STAMP(1);                              // prologue done
 
   if (warp == 4) {
     // ===== TMA producer + MMA issuer =====
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(qk_full + 8 * kb, 0);
         tc_fence_after();
+        AT_STAMP(8 + kb);                                  // Q | K block kb landed
         if (elect_one()) {
 #pragma unroll
           for (int t = 0; t < 3; ++t)
@@ -163,19 +172,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
     {
       mbar_wait(s_full, 0);
       tc_fence_after();
+      if (warp == 0) AT_STAMP(2);                          // S complete
       uint32_t sr[64];
       tmem_ld64(tmem_s + lane_addr, sr);
+      // exp(s - m) = 2^((s - m) log2 e): log2 e is folded into the scale and the exponential is one MUFU.EX2
+      // (2 ulp); expf() costs ~25 instructions per element on 16 active lanes - the softmax was 5 400 of the kernel's
+      // 20 000 cycles (profiles/r2/attention_timeline.md)
+      const float sl2 = p.scale * 1.4426950408889634f;
       float m = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        const float v = j < p.tk ? __uint_as_float(sr[j]) * p.scale : -INFINITY;
+        const float v = j < p.tk ? __uint_as_float(sr[j]) * sl2 : -INFINITY;
         sr[j] = __float_as_uint(v);
         m = fmaxf(m, v);
       }
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        const float e = j < p.tk ? expf(__uint_as_float(sr[j]) - m) : 0.f;
+        float e = 0.f;
+        if (j < p.tk) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__uint_as_float(sr[j]) - m));
         sum += e;
         sr[j] = __float_as_uint(e * P_SCALE);
       }
@@ -202,44 +217,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (warp == 0) AT_STAMP(3);                          // softmax done, P stored
     }
-    // ---- O: normalise, stage the 64 x 192 tile in shared memory (Q | K are dead once S is complete)
+    // ---- O: normalise and write straight from registers (thread = query row): 16-byte vectors per plane / float4 for
+    // fp32.  (Staging the tile in shared memory and copying it out row-contiguously cost 9 600 of 20 000 cycles.)
     mbar_wait(o_full, 0);
     tc_fence_after();
-    float* Os = reinterpret_cast<float*>(sm + Smem::OUT);
+    if (warp == 0) AT_STAMP(4);                            // O complete
+    const bool live = active && row < p.tq;
+    const long long grow = (long long)b * p.tq + row;
+    const bool vec16 = p.planes.ptr && ((p.planes.ld & 7) == 0) && ((p.planes.ps & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.planes.ptr) & 15) == 0);
+    __half* const prow = reinterpret_cast<__half*>(p.planes.ptr) + grow * p.planes.ld + h * HD;
+    float* const frow = p.out ? p.out + grow * p.ldo + h * HD : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < HD; c0 += 64) {
       uint32_t orr[64];
       tmem_ld64(tmem_o + lane_addr + c0, orr);
-      if (active) {
+      if (live) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4)
-          *reinterpret_cast<float4*>(Os + row * HD + c0 + j) =
-              make_float4(__uint_as_float(orr[j]) * inv, __uint_as_float(orr[j + 1]) * inv, __uint_as_float(orr[j + 2]) * inv,
-                          __uint_as_float(orr[j + 3]) * inv);
-      }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-    const bool vec_p = p.planes.ptr && ((p.planes.ld & 3) == 0) && ((p.planes.ps & 3) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(p.planes.ptr) & 7) == 0);
-    for (int i = threadIdx.x; i < p.tq * (HD / 4); i += 128) {
-      const int r = i / (HD / 4), c4 = i % (HD / 4);
-      const float4 v = *reinterpret_cast<const float4*>(Os + r * HD + c4 * 4);
-      const long long grow = (long long)b * p.tq + r;
-      if (p.out) *reinterpret_cast<float4*>(p.out + grow * p.ldo + h * HD + c4 * 4) = v;
-      if (p.planes.ptr) {
-        if (vec_p) pm_store_planes4_t<true>(p.planes, grow, h * HD + c4 * 4, v);
-        else {
-          pm_store_planes_t<true>(p.planes, grow, h * HD + c4 * 4, v.x); pm_store_planes_t<true>(p.planes, grow, h * HD + c4 * 4 + 1, v.y);
-          pm_store_planes_t<true>(p.planes, grow, h * HD + c4 * 4 + 2, v.z); pm_store_planes_t<true>(p.planes, grow, h * HD + c4 * 4 + 3, v.w);
+        for (int g8 = 0; g8 < 8; ++g8) {                   // 8 consecutive columns
+          float x[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) x[u] = __uint_as_float(orr[8 * g8 + u]) * inv;
+          if (frow) {
+            *reinterpret_cast<float4*>(frow + c0 + 8 * g8) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(frow + c0 + 8 * g8 + 4) = make_float4(x[4], x[5], x[6], x[7]);
+          }
+          if (p.planes.ptr) {
+            if (vec16) {
+              uint32_t h0[4], h1[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float a0 = x[2 * u] * PM_F16_ACT_SCALE, a1 = x[2 * u + 1] * PM_F16_ACT_SCALE;
+                const __half2 t0 = __floats2half2_rn(a0, a1);
+                const __half2 t1 = __floats2half2_rn(a0 - __low2float(t0), a1 - __high2float(t0));
+                h0[u] = *reinterpret_cast<const uint32_t*>(&t0);
+                h1[u] = *reinterpret_cast<const uint32_t*>(&t1);
+              }
+              *reinterpret_cast<uint4*>(prow + c0 + 8 * g8) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+              if (p.planes.nsplit > 1) *reinterpret_cast<uint4*>(prow + p.planes.ps + c0 + 8 * g8) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) pm_store_planes_t<true>(p.planes, grow, h * HD + c0 + 8 * g8 + u, x[u]);
+            }
+          }
         }
       }
     }
+    if (warp == 0) AT_STAMP(5);
   }
 
+  if (warp == 0) AT_STAMP(6);                              // outputs written
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) AT_STAMP(7);
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
@@ -265,7 +297,7 @@ extern "C" int pm_attention_tc(const uint16_t* Q, long long q_ps, long long q_bs
                                uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
   PM_REQUIRE(Q && K && V && (O || planes) && batch >= 0 && heads > 0);
   PM_TAKE_FMT(p_nsplit, f16);
-  PM_REQUIRE(!planes || f16);                              // fp16 planes in, fp16 planes out
+  PM_REQUIRE(!planes || (f16 && p_nsplit <= 2));           // fp16 planes in, (at most two) fp16 planes out
   PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, heads * head_dim, false));
   if (head_dim != HD || tq > T || tk > T || tq <= 0 || tk <= 0) return PM_EUNSUPPORTED;
   PM_REQUIRE(!O || (ldo & 3) == 0);
@@ -293,3 +325,11 @@ extern "C" int pm_attention_tc(const uint16_t* Q, long long q_ps, long long q_bs
   attention_tc_kernel<<<batch * heads, NTHREADS, kSmem, (cudaStream_t)stream>>>(mq, mk, mv, p);
   PM_LAUNCH_CHECK();
 }
+
+#ifdef PM_ATTN_TIMING
+extern "C" int pm_attn_timing_read(unsigned long long* host) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpyFromSymbol(host, pm_attn_stamps, sizeof(unsigned long long) * 16);
+}
+#endif

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) sts128(stage + (lane * ST + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
-      // identity == leaky with slope 1: one branch-free formula for none / relu / leaky / partial activation
+      // identity == leaky with slope 1: one branch-free (select) formula for none / relu / leaky / partial activation
       const float s0 = n < p.act_cols ? act_slope : 1.f, s1 = n + 1 < p.act_cols ? act_slope : 1.f;
       const float s2 = n + 2 < p.act_cols ? act_slope : 1.f, s3 = n + 3 < p.act_cols ? act_slope : 1.f;
       if (fast) {
@@ -317,10 +317,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             const float4 t = rres[i];
             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
           }
-          x.x = fmaxf(x.x, 0.f) + s0 * fminf(x.x, 0.f);
-          x.y = fmaxf(x.y, 0.f) + s1 * fminf(x.y, 0.f);
-          x.z = fmaxf(x.z, 0.f) + s2 * fminf(x.z, 0.f);
-          x.w = fmaxf(x.w, 0.f) + s3 * fminf(x.w, 0.f);
+          // compare-select, not fmaxf / fminf: those return the non-NaN operand and would turn the NaN an fp16 operand
+          // overflow leaves into 0, hiding it from the overflow guard (round 2: a 2e4x too loud input went unnoticed)
+          x.x = x.x < 0.f ? s0 * x.x : x.x;
+          x.y = x.y < 0.f ? s1 * x.y : x.y;
+          x.z = x.z < 0.f ? s2 * x.z : x.z;
+          x.w = x.w < 0.f ? s3 * x.w : x.w;
           if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off_f[i] + n) = x;
           if (p.out_bf16) {
             const PmPlanes P{p.out_bf16 + off_b[i], p.ob_ps, p.ldob, p.out_nsplit};
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(src + 4 * k) : "memory");
             y += k == 0 ? bias4.x : (k == 1 ? bias4.y : (k == 2 ? bias4.z : bias4.w));
             if (p.residual) y += p.residual[orr + n + k];
-            y = fmaxf(y, 0.f) + (k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) * fminf(y, 0.f);
+            y = y < 0.f ? (k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3))) * y : y;
             if (p.out_f32) p.out_f32[of + n + k] = y;
             if (P.ptr) pm_store_planes_t<F16>(P, 0, n + k, y);
           }

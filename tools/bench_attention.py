@@ -45,6 +45,17 @@ def main():
         us = timed(lambda: ops.attention_tc(qp, 0, qp, E, qp, 2 * E, bs, H, t, t, hd, nsplit=2, f32=f32))
         print(f"attention_tc_kernel planes{'+fp32' if f32 else '     '} out  {us:7.2f} us  {flop / us / 1e6:7.1f} TFLOP/s algorithmic "
               f"({3 * flop / us / 1e6:7.1f} of fp16 MMA work)")
+    if "--timeline" in sys.argv:          # instrumented build: python -m pantomatrix_b200.build --variant attn_timing -DPM_ATTN_TIMING
+        import ctypes
+        from pantomatrix_b200 import _lib
+        ops.attention_tc(qp, 0, qp, E, qp, 2 * E, bs, H, t, t, hd, nsplit=2)
+        buf = (ctypes.c_ulonglong * 16)()
+        assert _lib.load().pm_attn_timing_read(buf) == 0
+        v = list(buf)
+        names = ["entry", "prologue done", "S complete (warp 0)", "softmax done, P stored", "O complete", "outputs written", "-",
+                 "all warps done", "Q|K block 0 landed", "block 1", "block 2"]
+        for i, n in enumerate(names):
+            print(f"  {n:28s} +{(v[i] - v[0]):7d} cycles")
     ops.set_plane_format("bf16")
 
 
