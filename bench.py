@@ -356,7 +356,7 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
 
-    cap = CapturedPipeline(model, vqm, clips, N_SAMPLES) if args.graph else None
+    cap = CapturedPipeline(model, vqm, clips, N_SAMPLES, body_priority=bool(args.body_priority)) if args.graph else None
     if cap is not None:
         cap.audio.copy_(audio)
 
@@ -492,6 +492,7 @@ def main():
                     help="fp16x3 (default) and bf16x6 meet the fp32 parity gates; see DESIGN.md section 4")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0 skips the CPU timing (exploratory runs)")
     ap.add_argument("--extra", type=int, default=1, help="0 skips the other BASELINE configs (bs 1, CaMN, DisCo)")
+    ap.add_argument("--body-priority", type=int, default=1, help="capture the critical (body) chain on a high-priority stream")
     ap.add_argument("--graph", type=int, default=1, help="replay the step as one CUDA graph (1) or launch eagerly (0)")
     args = ap.parse_args()
     if args.impl == "reference":

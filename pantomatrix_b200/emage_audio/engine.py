@@ -473,12 +473,14 @@ class EmageEngine:
         kv, mem_face = self._fork_audio.run([body, face])
         return mem_face, kv
 
-    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body, dest=None):
+    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body, dest=None, use_audio=True):
         """One window of EmageAudioModel.forward (M.py:265-341) given the hoisted audio tensors.
         win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows).
         dest: optional dict name -> (bs, t, 256) fp32 view the final GEMM of that output writes into (the window's rows
         of inference()'s accumulated outputs), so nothing is copied afterwards."""
         dest = dest or {}
+        # use_audio=False (training-time ablation, M.py:310-311): the body's audio cross-attention output is multiplied
+        # by zero, i.e. motion_fea + 0 - the 8 cross layers are simply not run; the face branch still sees the audio.
         bs, t = (win_in.p.batch, win_in.p.rows) if isinstance(win_in, ops.Act) and win_in.f is None else _f32(win_in).shape[:2]
         E = self.E
         spk_f, spk_b = speaker_id_rows
@@ -500,9 +502,12 @@ class EmageEngine:
             fea = self.self_enc(x)
             fea = ops.add_rows(fea, self.pe, spk_b, ops.ROW_SPK, ops.ROW_PE, bs, t, E, nsplit=ns)
             x = fea
-            for i, (layer, kv) in enumerate(zip(self.cross, kv_body)):
-                x = layer(x, kv, want="fp" if i + 1 < len(self.cross) else "f")
-            fea = ops.add2(_f32(fea), _f32(x), nsplit=ns, f32=ns == 0)
+            if use_audio:
+                for i, (layer, kv) in enumerate(zip(self.cross, kv_body)):
+                    x = layer(x, kv, want="fp" if i + 1 < len(self.cross) else "f")
+                fea = ops.add2(_f32(fea), _f32(x), nsplit=ns, f32=ns == 0)
+            else:
+                fea = ops.add2(_f32(fea), torch.zeros_like(_f32(fea)), nsplit=ns, f32=ns == 0)
             lat = {p: self.to_latent[p](fea) for p in PARTS[1:]}
             others = {"upper": ("hands", "lower"), "hands": ("upper", "lower"), "lower": ("upper", "hands")}
 

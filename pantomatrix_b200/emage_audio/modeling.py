@@ -385,8 +385,6 @@ class EmageAudioModel(_EngineOwner):
     def forward(self, audio, speaker_id, masked_motion, mask, use_audio=True):
         """One window (M.py:265-341): audio (bs, n), speaker_id (bs,1) long, masked_motion / mask (bs,T,337)
         with mask==1 meaning "masked".  Returns the 8 rec_*/cls_* tensors (bs,T,256)."""
-        if not use_audio:
-            raise NotImplementedError("use_audio=False (training-time ablation, M.py:310-311) is off the inference path")
         eng = self._eng()
         dev = eng.device
         audio = audio.to(device=dev, dtype=torch.float32).contiguous()
@@ -399,7 +397,7 @@ class EmageAudioModel(_EngineOwner):
             ns = E._ns()
             win_in = ops.window_input(motion, mask, None, eng.mask_embedding, 0, t, 0, nsplit=ns, f32=ns == 0)
             mem_face, kv = eng.audio_phase(audio, 0, 0, 1, audio.shape[1], t)
-            return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv)
+            return eng.window(win_in, eng.speaker_rows(speaker_id.to(dev)), mem_face, kv, use_audio=use_audio)
         return E.guarded(run, lambda out: [out["cls_" + p] for p in E.PARTS])
 
     def inference(self, audio, speaker_id, vq_model, masked_motion=None, mask=None):

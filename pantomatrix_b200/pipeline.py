@@ -53,7 +53,7 @@ class CapturedPipeline:
     the next call).  Only the default-input form of the demo (masked_motion=None, mask=None) is captured.
     """
 
-    def __init__(self, model, motion_vq, batch: int, n_samples: int, warmup: int = 2):
+    def __init__(self, model, motion_vq, batch: int, n_samples: int, warmup: int = 2, body_priority: bool = True):
         self.model, self.vq = model, motion_vq
         dev = next(model.parameters()).device
         self.device = dev
@@ -69,7 +69,12 @@ class CapturedPipeline:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         before = ops.launch_count
-        with torch.cuda.graph(self.graph):
+        # The capture stream carries the longest dependency chain (the body stack: 1 + 8 layers per window); the face /
+        # refine / part branches fork onto default-priority side streams.  Capturing on a high-priority stream makes the
+        # kernel nodes of the critical chain win when both have thread blocks ready (a 96-CTA GEMM leaves 52 SMs free,
+        # which the other branch's blocks share): measured effect in profiles/README.md.
+        self.capture_stream = torch.cuda.Stream(device=dev, priority=-1) if body_priority else None
+        with torch.cuda.graph(self.graph, stream=self.capture_stream):
             self.latent, self.pred = generate(model, motion_vq, self.audio, self.speaker_id, ref_trans=self.ref_trans)
         self.kernels_per_replay = ops.launch_count - before
         self.nonfinite = generate.nonfinite                  # fp16 planes only: in-graph overflow flag (else None)

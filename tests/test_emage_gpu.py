@@ -138,6 +138,28 @@ def test_single_window_forward_matches_oracle(product, ckpt):
             assert torch.equal(got[k].argmax(-1).cpu(), v.argmax(-1)), k
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("tag,flag", [("audio", True), ("noaudio", False)])
+def test_forward_matches_reference_golden(product, golden_dir, tag, flag, precision):
+    """forward() against the unmodified reference's outputs, with and without use_audio (M.py:310-311)."""
+    import sys
+    from pantomatrix_b200.emage_audio import engine
+    sys.path.insert(0, golden_dir)
+    from make_golden_forward import BS, inputs
+    model, _ = product
+    g = np.load(os.path.join(golden_dir, "case_forward.npz"))
+    audio, motion, mask = inputs()
+    engine.set_precision(precision)
+    try:
+        got = model.forward(audio.cuda(), torch.zeros(BS, 1, dtype=torch.long).cuda(), motion.cuda(), mask.cuda(), use_audio=flag)
+    finally:
+        engine.set_precision("fp32")
+    for k, v in got.items():
+        np.testing.assert_allclose(v.cpu().numpy()[:, ::3], g[f"{tag}_{k}"], atol=1e-3 if k.startswith("rec_") else 2e-3, rtol=0, err_msg=k)
+        if k.startswith("cls_"):
+            assert np.array_equal(v.argmax(-1).cpu().numpy(), g[f"{tag}_idx_{k}"]), k
+
+
 def test_vq_decode_and_tokenise_match_oracle(product, ckpt):
     """EmageVQModel.decode (index and latent inputs, zero branches) and map2index (training-side
     tokenisation, all four L2-argmin lookups)."""

@@ -110,3 +110,21 @@ def test_oracle_tokenisation_matches_reference(golden_dir):
             np.testing.assert_allclose(float(fw["embedding_loss"]), float(g["embedding_loss_" + p]), rtol=1e-5)
             np.testing.assert_allclose(float(fw["perplexity"]), float(g["perplexity_" + p]), rtol=1e-5)
 
+
+
+@pytest.mark.parametrize("tag,flag", [("audio", True), ("noaudio", False)])
+def test_oracle_forward_matches_reference(tag, flag, ckpt, golden_dir):
+    """EmageAudioModel.forward on one window with user masked_motion / mask, with and without the audio cross-attention
+    (use_audio=False, M.py:310-311), against the unmodified reference (tests/golden/make_golden_forward.py)."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_forward import BS, inputs
+    sd, cfg, vq = ckpt
+    g = np.load(os.path.join(golden_dir, "case_forward.npz"))
+    audio, motion, mask = inputs()
+    with torch.no_grad():
+        got = O.emage_forward(sd, audio, torch.zeros(BS, 1, dtype=torch.long), motion, mask, use_audio=flag)
+    for k, v in got.items():
+        np.testing.assert_allclose(v.numpy()[:, ::3], g[f"{tag}_{k}"], atol=2e-4 if k.startswith("rec_") else 5e-4, rtol=0, err_msg=k)
+        if k.startswith("cls_"):
+            assert np.array_equal(v.argmax(-1).numpy(), g[f"{tag}_idx_{k}"]), k
