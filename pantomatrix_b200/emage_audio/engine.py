@@ -61,7 +61,8 @@ PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2, "bf16x6": 3, "fp16x3": 2}
 PLANE_FORMAT = {"fp16x3": "fp16"}
 DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "fp16x3")     # PM_EMAGE_PRECISION overrides
 _STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True,   # fork: overlap independent branches on side streams
-          "precision": DEFAULT_PRECISION}
+          "precision": DEFAULT_PRECISION,
+          "groups": int(__import__("os").environ.get("PM_EMAGE_GROUPS", "2"))}   # clip-group lanes of the window loop
 ops.set_plane_format(PLANE_FORMAT.get(DEFAULT_PRECISION, "bf16"))
 
 
@@ -452,7 +453,8 @@ class EmageEngine:
         self.out_proj["face"] = _Linear(sd, "face_out_proj")
         self.cls = {p: _MLP(sd, "motion_cls_" + p) for p in PARTS[1:]}
         self.cls["face"] = _MLP(sd, "face_cls")
-        self._fork_branch, self._fork_parts, self._fork_audio = _Fork(1), _Fork(2), _Fork(1)
+        self._fork_audio = _Fork(1)
+        self._lane_forks = {}          # clip-group lane -> (face || body fork, refine-parts fork): side streams are per lane
 
     # ------------------------------------------------------------------------------------------------
     def audio_phase(self, audio, offset, a_ws, windows, n_samples, t):
@@ -473,12 +475,18 @@ class EmageEngine:
         kv, mem_face = self._fork_audio.run([body, face])
         return mem_face, kv
 
-    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body, dest=None, use_audio=True):
+    def _forks(self, lane):
+        if lane not in self._lane_forks:
+            self._lane_forks[lane] = (_Fork(1), _Fork(2))
+        return self._lane_forks[lane]
+
+    def window(self, win_in, speaker_id_rows, mem_face_audio, kv_body, dest=None, use_audio=True, lane=0):
         """One window of EmageAudioModel.forward (M.py:265-341) given the hoisted audio tensors.
         win_in (bs,t,337) is already mask-embedded.  speaker_id_rows = (spk_face_rows, spk_body_rows).
         dest: optional dict name -> (bs, t, 256) fp32 view the final GEMM of that output writes into (the window's rows
         of inference()'s accumulated outputs), so nothing is copied afterwards."""
         dest = dest or {}
+        fork_branch, fork_parts = self._forks(lane)
         # use_audio=False (training-time ablation, M.py:310-311): the body's audio cross-attention output is multiplied
         # by zero, i.e. motion_fea + 0 - the 8 cross layers are simply not run; the face branch still sees the audio.
         bs, t = (win_in.p.batch, win_in.p.rows) if isinstance(win_in, ops.Act) and win_in.f is None else _f32(win_in).shape[:2]
@@ -521,11 +529,11 @@ class EmageEngine:
                 return {"rec_" + p: _f32(rec), "cls_" + p: self.cls[p](rec, out=dest.get("cls_" + p))}
 
             out = {}
-            for d in self._fork_parts.run([lambda p=p: refine(p) for p in PARTS[1:]]):
+            for d in fork_parts.run([lambda p=p: refine(p) for p in PARTS[1:]]):
                 out.update(d)
             return out
 
-        body, face = self._fork_branch.run([body_branch, face_branch])
+        body, face = fork_branch.run([body_branch, face_branch])
         body.update(face)
         return body
 
@@ -556,7 +564,7 @@ class VQEngine:
             self.global_enc = _ConvStack(sds["global"], "encoder", "encoder", n)
             self.global_dec = _ConvStack(sds["global"], "decoder", "decoder", n)
         self.device = self.codebook["face"].device
-        self._fork = _Fork(3)
+        self._forks = {}               # clip-group lane -> fork of the four part decoders
 
     def part_decode(self, p, index=None, latent=None):
         """EmageVQVAEConv.decode / decode_from_latent (M.py:56-70) -> (pose features, indices)."""
@@ -564,12 +572,14 @@ class VQEngine:
             index = ops.l2_argmin(latent, self.codebook[p], self.e2[p])
         return self.decoder[p](ops.gather_rows(self.codebook[p], index.contiguous(), nsplit=_ns())), index
 
-    def decode(self, index, latent, get_global_motion=False, ref_trans=None):
+    def decode(self, index, latent, get_global_motion=False, ref_trans=None, lane=0):
         """index/latent: dicts part -> tensor or None.  Returns the reference's 4-key dict (M.py:193)."""
         shape = next(t.shape[:2] for t in list(index.values()) + list(latent.values()) if t is not None)
         bs, t = int(shape[0]), int(shape[1])
         todo = [p for p in PARTS if index.get(p) is not None or latent.get(p) is not None]
-        done = self._fork.run([lambda p=p: self.part_decode(p, index.get(p), latent.get(p))[0] for p in todo])
+        if lane not in self._forks:
+            self._forks[lane] = _Fork(3)
+        done = self._forks[lane].run([lambda p=p: self.part_decode(p, index.get(p), latent.get(p))[0] for p in todo])
         feats = dict(zip(todo, done))
         expression, aa, m4 = ops.pose_compose(feats.get("face"), feats.get("upper"), feats.get("hands"),
                                               feats.get("lower"), bs, t, self.device)
@@ -674,22 +684,50 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
     # spill past the end: `pad` spare rows take that, and the result is the dense [:out_len] prefix (a copy only then).
     pad = max(0, max(off_t for off_t in [sum(k for _, _, k in plan[:i]) + (e - s) for i, (s, e, _) in enumerate(plan)]) - out_len)
     acc = {k + p: torch.empty(bs, out_len + pad, 256, device=dev) for k in ("rec_", "cls_") for p in PARTS}
-    seed = None                       # first window: the seed is motion[:, :pre] itself (M.py:379) - window_input keeps it
-    off = 0
-    for wi, (s, e, keep) in enumerate(plan):
-        t = e - s
-        win_in = ops.window_input(motion, full_mask, seed, engine.mask_embedding, s, t, pre, nsplit=_ns(), f32=_ns() == 0,
-                                  shape=(bs, length, ch))
-        mem_face, kv = hoisted[wi]
-        out = engine.window(win_in, spk, mem_face, kv, dest={k: v[:, off:off + t] for k, v in acc.items()})
-        off += keep
-        if wi + 1 < len(plan):                                                           # seed for the next window
-            nd = min(t, seed_decode_frames(cfg, vq))
-            tail = {k: v[:, t - nd:] for k, v in out.items()}                            # strided views, read in place
-            idx = {p: ops.row_argmax(tail["cls_" + p]) for p in PARTS}                   # M.py:398-401
-            index, latent = select_inputs(cfg, tail, idx)
-            dec = vq.decode(index, latent)
-            seed = dec["all_motion4inference"][:, nd - pre:]                             # M.py:418
+    # Clips are independent, and one window is a chain of ~150 dependent kernels whose GEMMs fill 48-288 of the 148 SMs:
+    # the clip batch is therefore split into `groups` lanes that run their window loops on separate streams, so that
+    # one lane's launch gaps, drains and epilogue tails are filled by the other lane's thread blocks (the hoisted audio
+    # phase above and the final decode stay batched).  Per-clip results do not depend on the grouping.
+    n_groups = max(1, min(int(_STATE.get("groups", 2)), bs // 8)) if torch.cuda.is_available() else 1
+    bounds = [bs * g // n_groups for g in range(n_groups + 1)]
+
+    def sl(x, g0, g1):                # clips g0..g1 of a (clips, ...) tensor, plane Act or None
+        if x is None:
+            return None
+        if isinstance(x, ops.Act):
+            pl = x.p
+            return ops.Act(None if x.f is None else x.f[g0:g1], None if pl is None else ops.Planes(pl.t[:, g0:g1], pl.rows, pl.ch, 0))
+        return x[g0:g1]
+
+    def run_lane(lane):
+        g0, g1 = bounds[lane], bounds[lane + 1]
+        nb = g1 - g0
+        spk_l = (spk[0][g0:g1], spk[1][g0:g1])
+        seed = None                   # first window: the seed is motion[:, :pre] itself (M.py:379) - window_input keeps it
+        off = 0
+        for wi, (s, e, keep) in enumerate(plan):
+            t = e - s
+            win_in = ops.window_input(sl(motion, g0, g1), sl(full_mask, g0, g1), seed, engine.mask_embedding, s, t, pre,
+                                      nsplit=_ns(), f32=_ns() == 0, shape=(nb, length, ch))
+            mem_face, kv = hoisted[wi]
+            out = engine.window(win_in, spk_l, sl(mem_face, g0, g1), [sl(k, g0, g1) for k in kv],
+                                dest={k: v[g0:g1, off:off + t] for k, v in acc.items()}, lane=lane)
+            off += keep
+            if wi + 1 < len(plan):                                                       # seed for the next window
+                nd = min(t, seed_decode_frames(cfg, vq))
+                tail = {k: v[:, t - nd:] for k, v in out.items()}                        # strided views, read in place
+                idx = {p: ops.row_argmax(tail["cls_" + p]) for p in PARTS}               # M.py:398-401
+                index, latent = select_inputs(cfg, tail, idx)
+                dec = vq.decode(index, latent, lane=lane)
+                seed = dec["all_motion4inference"][:, nd - pre:]                         # M.py:418
+        return None
+
+    if n_groups == 1:
+        run_lane(0)
+    else:
+        if getattr(engine, "_fork_lanes", None) is None or engine._fork_lanes.n_side != n_groups - 1:
+            engine._fork_lanes = _Fork(n_groups - 1)
+        engine._fork_lanes.run([lambda lane=lane: run_lane(lane) for lane in range(n_groups)])
     if pad:
         acc = {k: v[:, :out_len].contiguous() for k, v in acc.items()}
     return acc
