@@ -203,8 +203,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float a0 = __uint_as_float(sr[8 * c + 2 * u]), a1 = __uint_as_float(sr[8 * c + 2 * u + 1]);
-            const __half2 h0 = __floats2half2_rn(a0, a1);
-            const __half2 h1 = __floats2half2_rn(a0 - __low2float(h0), a1 - __high2float(h0));
+            const float f0 = pm_f16_head(a0), f1 = pm_f16_head(a1);       // exact in fp16: no conversion back (pm_common.cuh)
+            const __half2 h0 = __floats2half2_rn(f0, f1);
+            const __half2 h1 = __floats2half2_rn(a0 - f0, a1 - f1);
             hi[u] = *reinterpret_cast<const uint32_t*>(&h0);
             lo[u] = *reinterpret_cast<const uint32_t*>(&h1);
           }
@@ -250,8 +251,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_tc_kernel(const __grid_
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const float a0 = x[2 * u] * PM_F16_ACT_SCALE, a1 = x[2 * u + 1] * PM_F16_ACT_SCALE;
-                const __half2 t0 = __floats2half2_rn(a0, a1);
-                const __half2 t1 = __floats2half2_rn(a0 - __low2float(t0), a1 - __high2float(t0));
+                const float f0 = pm_f16_head(a0), f1 = pm_f16_head(a1);
+                const __half2 t0 = __floats2half2_rn(f0, f1);
+                const __half2 t1 = __floats2half2_rn(a0 - f0, a1 - f1);
                 h0[u] = *reinterpret_cast<const uint32_t*>(&t0);
                 h1[u] = *reinterpret_cast<const uint32_t*>(&t1);
               }

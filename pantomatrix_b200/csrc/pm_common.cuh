@@ -86,6 +86,17 @@ __device__ __forceinline__ void pm_split3(float v, __nv_bfloat16 (&p)[3]) {
   const bool flag_var = ((nsplit_var) & PM_FMT_F16) != 0;          \
   (nsplit_var) &= 0xff
 
+// Two-plane fp16 split of v (already pre-scaled): plane 0 = v rounded to 11 significant bits, plane 1 = the remainder.
+// Plane 0 is formed with integer ops on the fp32 bit pattern (add half an ulp of the 10-bit mantissa, clear the 13 low
+// bits: round-half-away, exponent carry included) - the result is exactly representable in fp16, so its conversion is
+// exact and the remainder v - f0 needs no conversion BACK from fp16.  Those back-conversions run at a fraction of the
+// FP32 rate and made every plane-writing epilogue conversion-bound (GEMM epilogue 7 500 cycles with planes against
+// 5 000 without, profiles/r2/gemm_timeline_fp16.txt).  (Below 2^-14 plane 0 would be an fp16 subnormal, which the
+// tensor core flushes anyway.)
+__device__ __forceinline__ float pm_f16_head(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x00001000u) & 0xFFFFE000u);
+}
+
 // Successive planes are peeled off a running remainder: no dynamically indexed temporaries (they would live in
 // local memory).
 template <bool F16>
@@ -93,10 +104,16 @@ __device__ __forceinline__ void pm_store_planes_t(const PmPlanes& P, long long r
   if constexpr (F16) {
     __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
     v *= PM_F16_ACT_SCALE;
-    for (int pl = 0; pl < P.nsplit; ++pl) {
-      const __half h = __float2half_rn(v);
-      o[(long long)pl * P.ps] = h;
-      v -= __half2float(h);
+    if (P.nsplit <= 2) {
+      const float f0 = P.nsplit == 2 ? pm_f16_head(v) : v;
+      o[0] = __float2half_rn(f0);
+      if (P.nsplit == 2) o[P.ps] = __float2half_rn(v - f0);
+    } else {
+      for (int pl = 0; pl < P.nsplit; ++pl) {
+        const __half h = __float2half_rn(v);
+        o[(long long)pl * P.ps] = h;
+        v -= __half2float(h);
+      }
     }
   } else {
     __nv_bfloat16* o = P.ptr + row * P.ld + c;
@@ -117,6 +134,17 @@ __device__ __forceinline__ void pm_store_planes4_t(const PmPlanes& P, long long 
   if constexpr (F16) {
     __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
     v.x *= PM_F16_ACT_SCALE; v.y *= PM_F16_ACT_SCALE; v.z *= PM_F16_ACT_SCALE; v.w *= PM_F16_ACT_SCALE;
+    if (P.nsplit == 2) {
+      const float4 f = make_float4(pm_f16_head(v.x), pm_f16_head(v.y), pm_f16_head(v.z), pm_f16_head(v.w));
+      const __half2 a0 = __floats2half2_rn(f.x, f.y), a1 = __floats2half2_rn(f.z, f.w);                       // exact
+      const __half2 b0 = __floats2half2_rn(v.x - f.x, v.y - f.y), b1 = __floats2half2_rn(v.z - f.z, v.w - f.w);
+      uint2 w0, w1;
+      w0.x = *reinterpret_cast<const uint32_t*>(&a0); w0.y = *reinterpret_cast<const uint32_t*>(&a1);
+      w1.x = *reinterpret_cast<const uint32_t*>(&b0); w1.y = *reinterpret_cast<const uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(o) = w0;
+      *reinterpret_cast<uint2*>(o + P.ps) = w1;
+      return;
+    }
     for (int pl = 0; pl < P.nsplit; ++pl) {
       const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
       uint2 w;

@@ -38,6 +38,9 @@ def main():
     print(f"{'shape':28s} ns out  CTAs | cycles after entry (mean over CTAs): " + " | ".join(NAMES) +
           " || span max (cyc) | period us | span us @period clock")
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    fp16 = len(sys.argv) > 2 and sys.argv[2] == "fp16"          # the default engine: two fp16 planes
+    if fp16:
+        ops.set_plane_format("fp16")
     for name, b, rows, cin, cout, taps, pad in SHAPES:
         if only and only not in name:
             continue
@@ -46,11 +49,14 @@ def main():
         w = (torch.randn(taps, cout, cin, generator=g) / math.sqrt(cin * taps)).cuda()
         bias = torch.zeros(cout, device="cuda")
         rows_out = rows + 2 * pad - taps + 1
-        for ns in (1, 3):
+        for ns in ((2,) if fp16 else (1, 3)):
             a, pw = ops.split_bf16(x, ns), ops.PackedW(w, ns)
-            for out_mode in ("f32", "f+p"):
-                kw = dict(rows_out=rows_out, pad=pad, act=ops.ACT_RELU, out_nsplit=ns if out_mode == "f+p" else 0,
-                          out=torch.empty(b, rows_out, cout, device="cuda"))
+            for out_mode in ("f32", "f+p", "p"):
+                kw = dict(rows_out=rows_out, pad=pad, act=ops.ACT_RELU, out_nsplit=0 if out_mode == "f32" else ns)
+                if out_mode == "p":
+                    kw["want_f32"] = False
+                else:
+                    kw["out"] = torch.empty(b, rows_out, cout, device="cuda")
                 for _ in range(3):
                     ops.tapgemm_tc(a, pw, bias, **kw)
                 graph = torch.cuda.CUDAGraph()
