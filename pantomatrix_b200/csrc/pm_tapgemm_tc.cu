@@ -65,13 +65,21 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 #include "pm_tc_ptx.cuh"   // PTX wrappers: mbarrier, TMA, tcgen05
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, bool F16>
+// CG2 = the CTA-pair form (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster, neighbours along the row-tile axis, work
+// on one 256 x BN tile.  Each keeps its own 128 rows of A and its 128 x BN accumulators, but only HALF of the W tile
+// (BN / 2 weight rows); the leader's MMAs (M = 256) read both halves.  Why: with two fp16 planes a k-block brings
+// 64 KB into shared memory for 12 MMAs of 64 cycles - 83 B / cycle against the ~64 B / cycle an SM can take in from
+// L2, so the single-CTA mainloop is fill-bound (1 058 cycles per k-block instead of 768, profiles/r2/gemm_timeline_fp16.txt);
+// the pair needs 48 KB per CTA and k-block.
+template <int BN, bool F16, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const TcParams p) {
-  constexpr int W_TILE_BYTES = BN * BK * 2;
+  constexpr int W_ROWS_CTA = CG2 ? BN / 2 : BN;     // weight rows this CTA stages per k-block and plane
+  constexpr int W_TILE_BYTES = W_ROWS_CTA * BK * 2;
   // instruction descriptor: D = f32; A and B format field 1 = bf16, 0 = fp16; K-major A and B; N >> 3; M >> 4
-  constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((CG2 ? 2 * BM : BM) >> 4) << 24);
   // Three fp32 accumulators in TMEM: two "main" ones that take the p0*p0 products of alternate k-iterations
   // and one "correction" accumulator for every cross product.  The tensor core aligns and TRUNCATES addends to
   // the accumulator's exponent on every MMA, a biased error ~2^-25 |acc| per instruction; keeping the 2^-8-scaled
@@ -96,23 +104,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   const int n0 = blockIdx.y * BN;
   const int b0 = blockIdx.z * p.NB;
   const int n_iter = p.taps * p.kblocks;
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), CG2 ? 2 : 1);          // pair: the leader's expect_tx arrival + the peer's arrival
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(acc_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG2) {                                       // one warp of EACH CTA of the pair, same shared-memory slot
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();     // the peer's barriers exist before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) PM_STAMP(1);                                   // prologue done (barriers, TMEM, descriptors)
@@ -143,12 +158,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         const uint32_t bar = smem_u32(&full_bar[s]);
         uint8_t* st = tiles + (size_t)s * stage_bytes;
         if (elect_one()) {
-        mbar_expect_tx(bar, tx);
+        if constexpr (CG2) {
+          // both CTAs' bytes land on the LEADER's barrier: it expects 2 x tx, the peer contributes a plain arrival
+          if (cta_rank == 0) mbar_expect_tx(bar, 2 * tx);
+          else mbar_arrive_remote(bar, 0);
+        } else {
+          mbar_expect_tx(bar, tx);
+        }
         for (int pl = 0; pl < p.nsplit; ++pl) {
           const uint32_t a_dst = smem_u32(st + pl * A_TILE_BYTES);
           const uint32_t w_dst = smem_u32(st + p.nsplit * A_TILE_BYTES + pl * W_TILE_BYTES);
-          tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
-          tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
+          if constexpr (CG2) {
+            tma_load_4d_cg2(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+            tma_load_3d_cg2(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0 + (int)cta_rank * W_ROWS_CTA, pl);
+          } else {
+            tma_load_4d(a_dst, &map_a, bar, kb * BK, l0 + tap - p.pad, b0, pl);
+            tma_load_3d(w_dst, &map_w, bar, kb * BK, tap * p.w_rows + n0, pl);
+          }
         }
         }
         __syncwarp();
@@ -157,7 +183,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (pair: the leader CTA only; the peer's warp 1 only owns its TMEM allocation) =====
+    if (cta_rank == 0)
     // One thread feeds the tensor core, so its own instruction stream must stay far below the 64 cycles a
     // 128x128x16 MMA takes.  Measured: with per-MMA descriptor construction, runtime div/mod for the stage ring
     // and a clock-reading wait loop this thread was THE bottleneck (the mainloop ran at the same speed with all TMA
@@ -165,6 +192,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     // adding to a precomputed 64-bit base, product loops specialised per split mode and fully unrolled.
     {
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if constexpr (CG2) tc_mma_cg2(d, a, b, idesc, acc);
+        else tc_mma_bf16(d, a, b, idesc, acc);
+      };
+      auto commit = [](uint32_t bar) {
+        if constexpr (CG2) tc_commit_cg2(bar);               // arrives in both CTAs of the pair
+        else tc_commit(bar);
+      };
       const uint32_t tiles_u32 = smem_u32(tiles);
       const uint32_t d_corr = tmem_base + 2 * ACC;
       uint32_t first_main0 = 1, first_main1 = 1, first_corr = 1;     // 1 until the accumulator has been written once
@@ -184,32 +219,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         // cross products first (small -> large), into the correction accumulator
         if (p.nsplit == 3) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + 2 * W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_corr, a0 + k * K_ST, w0 + 2 * W_PL + k * K_ST, IDESC, (k | (int)(first_corr ^ 1u)) != 0);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + W_PL + k * K_ST, IDESC, 1);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_corr, a0 + A_PL + k * K_ST, w0 + W_PL + k * K_ST, IDESC, 1);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + 2 * A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_corr, a0 + 2 * A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
         }
         if (p.nsplit >= 2) {
           const uint32_t fresh = p.nsplit == 3 ? 0u : first_corr;      // with 3 planes the block above already wrote it
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + k * K_ST, w0 + W_PL + k * K_ST, IDESC, (k | (int)(fresh ^ 1u)) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_corr, a0 + k * K_ST, w0 + W_PL + k * K_ST, IDESC, (k | (int)(fresh ^ 1u)) != 0);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_corr, a0 + A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_corr, a0 + A_PL + k * K_ST, w0 + k * K_ST, IDESC, 1);
         }
         {
           const uint32_t first = odd ? first_main1 : first_main0;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) tc_mma_bf16(d_main, a0 + k * K_ST, w0 + k * K_ST, IDESC, (k | (int)(first ^ 1u)) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) mma(d_main, a0 + k * K_ST, w0 + k * K_ST, IDESC, (k | (int)(first ^ 1u)) != 0);
         }
-        tc_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
+        commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs have read it
         }
         __syncwarp();
         if (p.nsplit >= 2) first_corr = 0;
         if (it & 1) first_main1 = 0; else first_main0 = 0;
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      if (n_iter > 0 && elect_one()) tc_commit(smem_u32(acc_bar));      // accumulator complete
+      if (n_iter > 0 && elect_one()) commit(smem_u32(acc_bar));      // accumulator complete
       PM_STAMP(3);                                                // all MMAs issued
     }
   } else {
@@ -362,9 +397,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 0) PM_STAMP(6);                                     // all warps done
+  if constexpr (CG2) cluster_sync_all();    // neither CTA frees TMEM or leaves while the peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -398,9 +435,9 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, bool F16>
+template <int BN, bool F16, bool CG2>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
-  const int stage_bytes = p.nsplit * (A_TILE_BYTES + BN * BK * 2);
+  const int stage_bytes = p.nsplit * (A_TILE_BYTES + (CG2 ? BN / 2 : BN) * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
   int stages = (env_kb * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -409,11 +446,28 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
   static unsigned long long configured = 0;       // per template instantiation, one bit per device
   if (pm_first_use_on_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { configured = 0; return (int)e; }
   }
-  tapgemm_tc_kernel<BN, F16><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
-  PM_LAUNCH_CHECK();
+  if constexpr (CG2) {                      // CTA pairs: 2-CTA clusters along the row-tile axis
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2>, ma, mw, p);
+    return e == cudaSuccess ? PM_OK : (int)e;
+  } else {
+    tapgemm_tc_kernel<BN, F16, CG2><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
+    PM_LAUNCH_CHECK();
+  }
 }
 
 }  // namespace
@@ -452,6 +506,9 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   // programmatic dependent launch (35.2 vs 34.7 ms): profiles/README.md.
   int BNsel = cout <= 64 ? 64 : 128;
   PM_REQUIRE(w_rows % BNsel == 0);
+  // CTA pairs (cta_group::2) where the row-tile grid is even: two fp16 planes, 128-column tiles, 128-row tiles.
+  static const bool cg2_on = !(getenv("PM_TC_CG2") && atoi(getenv("PM_TC_CG2")) == 0);      // A/B switch (tools)
+  const bool cg2 = cg2_on && f16 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0;
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
@@ -478,17 +535,18 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
     const long long ps_el = nsplit > 1 ? w_ps : (long long)taps * w_rows * ldw;
     cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps * w_rows, (cuuint64_t)nsplit};
     cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(cg2 ? BNsel / 2 : BNsel), 1};      // pair: each CTA stages half of the W tile
     if (!encode_map(&mw, W, 3, dims, strides, box, f16)) return PM_EBADARG;
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
   if (f16) {
-    if (BNsel == 64) return launch<64, true>(ma, mw, p, grid, (cudaStream_t)stream);
-    return launch<128, true>(ma, mw, p, grid, (cudaStream_t)stream);
+    if (cg2) return launch<128, true, true>(ma, mw, p, grid, (cudaStream_t)stream);
+    if (BNsel == 64) return launch<64, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
+    return launch<128, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
   }
-  if (BNsel == 64) return launch<64, false>(ma, mw, p, grid, (cudaStream_t)stream);
-  return launch<128, false>(ma, mw, p, grid, (cudaStream_t)stream);
+  if (BNsel == 64) return launch<64, false, false>(ma, mw, p, grid, (cudaStream_t)stream);
+  return launch<128, false, false>(ma, mw, p, grid, (cudaStream_t)stream);
 }
 
 #ifdef PM_TC_TIMING
