@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), CG2 ? 2 : 1);          // pair: the leader's expect_tx arrival + the peer's arrival
+      mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(acc_bar), 1);
@@ -159,9 +159,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid
         uint8_t* st = tiles + (size_t)s * stage_bytes;
         if (elect_one()) {
         if constexpr (CG2) {
-          // both CTAs' bytes land on the LEADER's barrier: it expects 2 x tx, the peer contributes a plain arrival
+          // Both CTAs' bytes land on the LEADER's barrier, which expects 2 x tx; the peer's barrier is unused.  (The
+          // peer cannot run a phase ahead: it reuses a stage only after the leader's MMAs of the previous use have
+          // committed.  A cluster-scope release arrive from the peer per k-block was tried first and serialised the
+          // peer's producer: 1 430 cycles per k-block whatever the work.)
           if (cta_rank == 0) mbar_expect_tx(bar, 2 * tx);
-          else mbar_arrive_remote(bar, 0);
         } else {
           mbar_expect_tx(bar, tx);
         }
@@ -508,7 +510,11 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   PM_REQUIRE(w_rows % BNsel == 0);
   // CTA pairs (cta_group::2) where the row-tile grid is even: two fp16 planes, 128-column tiles, 128-row tiles.
   static const bool cg2_on = !(getenv("PM_TC_CG2") && atoi(getenv("PM_TC_CG2")) == 0);      // A/B switch (tools)
-  const bool cg2 = cg2_on && f16 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0;
+  // Measured (profiles/r2/gemm_microbench_fp16_pairs.txt, M = 2048, N = 768): K = 768 12.4 vs 13.5 us, K = 1536 18.1 vs
+  // 20.8, K = 3072 29.0 vs 35.5 (906 instead of 1 184 cycles per k-block: MMA-bound); K <= 256 is a few hundred ns
+  // slower (cluster barriers in prologue and teardown), hence the k-block threshold.
+  const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0 &&
+                   taps * ((cin + BK - 1) / BK) >= 6;
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;

@@ -43,7 +43,7 @@ def main():
         w = (torch.randn(taps, cout, cin, generator=g) / math.sqrt(cin * taps)).cuda()
         bias = torch.zeros(cout, device="cuda")
         rows_out = rows + 2 * pad - taps + 1
-        for ns in ((2,) if fp16 else (1, 2, 3)):
+        for ns in ((tuple(int(a) for a in sys.argv[3:]) or (2,)) if fp16 else (1, 2, 3)):
             a = ops.split_bf16(x, ns)
             pw = ops.PackedW(w, ns)
             for out_mode in ("f32", "f+p"):
