@@ -65,8 +65,8 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 #include "pm_tc_ptx.cuh"   // PTX wrappers: mbarrier, TMA, tcgen05
 
 // ---------------------------------------------------------------------------------------------------
-// CG2 = the CTA-pair form (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster, neighbours along the row-tile axis, work
-// on one 256 x BN tile.  Each keeps its own 128 rows of A and its 128 x BN accumulators, but only HALF of the W tile
+// CG2 = the CTA-pair form (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster, neighbours along the row-tile (or, for
+// batch-tiled convs, the clip-tile) axis, work on one 256 x BN tile.  Each keeps its own 128 rows of A and its 128 x BN accumulators, but only HALF of the W tile
 // (BN / 2 weight rows); the leader's MMAs (M = 256) read both halves.  Why: with two fp16 planes a k-block brings
 // 64 KB into shared memory for 12 MMAs of 64 cycles - 83 B / cycle against the ~64 B / cycle an SM can take in from
 // L2, so the single-CTA mainloop is fill-bound (1 058 cycles per k-block instead of 768, profiles/r2/gemm_timeline_fp16.txt);
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
 
 // ---------------------------------------------------------------------------------------------------
 template <int BN, bool F16, bool CG2>
-int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st, int pair_axis = 0) {
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + (CG2 ? BN / 2 : BN) * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
   int stages = (env_kb * 1024) / stage_bytes;
@@ -459,9 +459,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = pair_axis == 0 ? 2 : 1;       // the pair: two row tiles (x) or two clip tiles (z) of one N tile
     attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.z = pair_axis == 2 ? 2 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2>, ma, mw, p);
@@ -513,8 +513,9 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   // Measured (profiles/r2/gemm_microbench_fp16_pairs.txt, M = 2048, N = 768): K = 768 12.4 vs 13.5 us, K = 1536 18.1 vs
   // 20.8, K = 3072 29.0 vs 35.5 (906 instead of 1 184 cycles per k-block: MMA-bound); K <= 256 is a few hundred ns
   // slower (cluster barriers in prologue and teardown), hence the k-block threshold.
-  const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0 &&
-                   taps * ((cin + BK - 1) / BK) >= 6;
+  const int gx = pm_cdiv(rows_out, R), gz = pm_cdiv(batch, NB);
+  const int pair_axis = gx % 2 == 0 ? 0 : (gz % 2 == 0 ? 2 : -1);      // two M tiles that share the W tile
+  const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && pair_axis >= 0 && taps * ((cin + BK - 1) / BK) >= 6;
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
@@ -547,7 +548,7 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
   if (f16) {
-    if (cg2) return launch<128, true, true>(ma, mw, p, grid, (cudaStream_t)stream);
+    if (cg2) return launch<128, true, true>(ma, mw, p, grid, (cudaStream_t)stream, pair_axis);
     if (BNsel == 64) return launch<64, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
     return launch<128, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
   }
