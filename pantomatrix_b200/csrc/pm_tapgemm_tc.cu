@@ -65,8 +65,8 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 #include "pm_tc_ptx.cuh"   // PTX wrappers: mbarrier, TMA, tcgen05
 
 // ---------------------------------------------------------------------------------------------------
-// CG2 = the CTA-pair form (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster, neighbours along the row-tile (or, for
-// batch-tiled convs, the clip-tile) axis, work on one 256 x BN tile.  Each keeps its own 128 rows of A and its 128 x BN accumulators, but only HALF of the W tile
+// CG2 = the CTA-pair form (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster, neighbours along the row-tile axis, work
+// on one 256 x BN tile.  Each keeps its own 128 rows of A and its 128 x BN accumulators, but only HALF of the W tile
 // (BN / 2 weight rows); the leader's MMAs (M = 256) read both halves.  Why: with two fp16 planes a k-block brings
 // 64 KB into shared memory for 12 MMAs of 64 cycles - 83 B / cycle against the ~64 B / cycle an SM can take in from
 // L2, so the single-CTA mainloop is fill-bound (1 058 cycles per k-block instead of 768, profiles/r2/gemm_timeline_fp16.txt);
@@ -513,9 +513,12 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   // Measured (profiles/r2/gemm_microbench_fp16_pairs.txt, M = 2048, N = 768): K = 768 12.4 vs 13.5 us, K = 1536 18.1 vs
   // 20.8, K = 3072 29.0 vs 35.5 (906 instead of 1 184 cycles per k-block: MMA-bound); K <= 256 is a few hundred ns
   // slower (cluster barriers in prologue and teardown), hence the k-block threshold.
-  const int gx = pm_cdiv(rows_out, R), gz = pm_cdiv(batch, NB);
-  const int pair_axis = gx % 2 == 0 ? 0 : (gz % 2 == 0 ? 2 : -1);      // two M tiles that share the W tile
-  const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && pair_axis >= 0 && taps * ((cin + BK - 1) / BK) >= 6;
+  // Pairs are formed along the row-tile axis only.  (Pairing clip tiles of the batch-tiled small-R convs along z was
+  // tried and failed the golden parity tests on the first run; it was not pursued - those convs are a few per cent
+  // of the step.)
+  const int pair_axis = 0;
+  const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0 &&
+                   taps * ((cin + BK - 1) / BK) >= 6;
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
