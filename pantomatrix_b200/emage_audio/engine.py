@@ -62,7 +62,9 @@ PLANE_FORMAT = {"fp16x3": "fp16"}
 DEFAULT_PRECISION = __import__("os").environ.get("PM_EMAGE_PRECISION", "fp16x3")     # PM_EMAGE_PRECISION overrides
 _STATE = {"nsplit": PRECISIONS[DEFAULT_PRECISION], "fork": True,   # fork: overlap independent branches on side streams
           "precision": DEFAULT_PRECISION,
-          "groups": int(__import__("os").environ.get("PM_EMAGE_GROUPS", "2"))}   # clip-group lanes of the window loop
+          # clip-group lanes of the window loop (run_inference).  Measured at batch 32: 1 lane 19.91 ms, 2 lanes 19.59,
+          # 4 lanes 19.49 per step - a 2 % gain for 2-4x the kernel launches, so one lane is the default.
+          "groups": int(__import__("os").environ.get("PM_EMAGE_GROUPS", "1"))}
 ops.set_plane_format(PLANE_FORMAT.get(DEFAULT_PRECISION, "bf16"))
 
 
@@ -688,7 +690,7 @@ def run_inference(engine: EmageEngine, vq: VQEngine, audio, speaker_id, masked_m
     # the clip batch is therefore split into `groups` lanes that run their window loops on separate streams, so that
     # one lane's launch gaps, drains and epilogue tails are filled by the other lane's thread blocks (the hoisted audio
     # phase above and the final decode stay batched).  Per-clip results do not depend on the grouping.
-    n_groups = max(1, min(int(_STATE.get("groups", 2)), bs // 8)) if torch.cuda.is_available() else 1
+    n_groups = max(1, min(int(_STATE.get("groups", 1)), bs // 8)) if torch.cuda.is_available() else 1
     bounds = [bs * g // n_groups for g in range(n_groups + 1)]
 
     def sl(x, g0, g1):                # clips g0..g1 of a (clips, ...) tensor, plane Act or None
