@@ -38,6 +38,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // For waits that are expected to be long (a pipeline stage waiting for a slower one): back off between probes so that
 // the waiting warps do not eat the issue slots of the working ones.
+template <int SLEEP_NS = 40>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (true) {
@@ -48,7 +49,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return;
-    __nanosleep(40);
+    __nanosleep(SLEEP_NS);
     if (++spins > 50000000u) __trap();            // > 2 s: a protocol bug must become an error, never a hung GPU
   }
 }

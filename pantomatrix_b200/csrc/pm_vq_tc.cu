@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
         // The previous tile's MMAs must have read the A tile before it is overwritten.  They release it in two halves
         // (k-blocks 0-1, then 2-3), so the first halves of this batch's rows are stored while the MMAs of k-blocks 2-3
         // still run.
-        if (half == 0) mbar_wait_relaxed(a_empty, (uint32_t)(it & 1) ^ 1u);
+        if (half == 0) mbar_wait_relaxed<20>(a_empty, (uint32_t)(it & 1) ^ 1u);
         if (warp == 0) VQ_ADD(1, t_we);
         VQ_T(t_cv);
         if ((lane & 3) == 0) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
           const uint32_t dst = dst0 + (uint32_t)(j * 128 + ((((lane & 15) >> 1) ^ j) << 4) + (lane & 1) * 8);
           sts64(dst, pack_h2(v[j][0].x * sc, v[j][0].y * sc), pack_h2(v[j][0].z * sc, v[j][0].w * sc));
         }
-        if (half == 0) mbar_wait_relaxed(a_empty_hi, (uint32_t)(it & 1) ^ 1u);
+        if (half == 0) mbar_wait_relaxed<20>(a_empty_hi, (uint32_t)(it & 1) ^ 1u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                      // k-blocks 2 / 3
           const float sc = __shfl_sync(0xffffffffu, sc_own, 4 * j);
@@ -312,10 +312,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) l2_argmin_tc_kernel(
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       VQ_T(t_m0);
-      mbar_wait_relaxed(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
+      mbar_wait(acc_empty + 8 * buf, (uint32_t)((it >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator (one warp: tight spin)
       VQ_ADD(3, t_m0);
       VQ_T(t_m1);
-      mbar_wait_relaxed(a_full, (uint32_t)(it & 1));
+      mbar_wait(a_full, (uint32_t)(it & 1));
       VQ_ADD(4, t_m1);
       VQ_CNT(11, 1);
       tc_fence_after();
