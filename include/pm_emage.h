@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 4
+#define PM_ABI_VERSION 5
 #define PM_FMT_F16 0x100
 int pm_abi_version(void);
 /* cudaMemsetAsync on `stream` (a memset node under graph capture, not a kernel): zeroed slack rows, flags */
@@ -81,11 +81,15 @@ int pm_split_bf16(const float* x, long long x_bs, int ldx, int batch, int rows, 
 /* ---- WavEncoder stem: first BasicBlock's conv1 and downsample conv on the raw waveform (Cin = 1) --
  * sequence (b, w) starts at audio + b*a_bs + w*a_ws and is n_samples long; k=15, stride 5, pad 1600.
  * Outputs are window-major: row block (w*batch + b) of (windows*batch, rows_out, cout).
- * y1 = LeakyReLU_0.01(conv1*bn1), sc = downsample conv*bn (both BN-folded): P.py:285-291,301. */
+ * y1 = LeakyReLU_0.01(conv1*bn1), sc = downsample conv*bn (both BN-folded): P.py:285-291,301.
+ * y1 goes out as fp32 (`y1`, nullable) and / or as the next GEMM's operand planes (`planes`, nullable; dense rows of
+ * p_ld elements, plane stride p_ps, p_nsplit | PM_FMT_F16 as for pm_add_layernorm_f32); at least one of the two.
+ * cout 32 or 64, ksize 15; anything else returns PM_EUNSUPPORTED. */
 int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_ws, int batch, int windows, int n_samples,
                     const float* w1, const float* b1, const float* wd, const float* bd, int cout,
                     int ksize, int stride, int pad, int rows_out, float slope,
-                    float* y1, float* sc, void* stream);
+                    float* y1, float* sc,
+                    uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream);
 
 /* ---- LayerNorm(x + r) * gamma + beta over the last dim (r nullable): post-norm residual of
  * nn.TransformerEncoderLayer / DecoderLayer (M.py:238-250), eps 1e-5.  ch must be a multiple of 128 <= 1024 */

@@ -24,7 +24,7 @@ SIGNATURES = {
     "pm_tapgemm_tc": [_p, _ll, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _i, _i, _p, _ll, _i,
                       _i, _i, _f, _f, _p, _ll, _i, _p, _ll, _ll, _i, _i, _p, _ll, _p],
     "pm_split_bf16": [_p, _ll, _i, _i, _i, _i, _p, _ll, _ll, _i, _i, _p],
-    "pm_wav_stem_f32": [_p, _ll, _ll, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p],
+    "pm_wav_stem_f32": [_p, _ll, _ll, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _ll, _i, _i, _p],
     "pm_add_layernorm_f32": [_p, _p, _p, _p, _p, _ll, _i, _f, _p, _ll, _i, _i, _p],
     "pm_attention_f32": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _i, _i, _p],
     "pm_attention_tc": [_p, _ll, _ll, _i, _i, _i, _p, _ll, _ll, _i, _i, _i, _p, _ll, _ll, _i, _i, _i,

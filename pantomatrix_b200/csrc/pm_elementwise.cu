@@ -6,46 +6,115 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
-// WavEncoder stem (Cin = 1): one thread per (row, channel); both convs share the 15 input samples.
+// WavEncoder stem (Cin = 1): both convs of the first block share the input samples.
+//
+// Round 1 ran one thread per (row, channel) with weights and samples in shared memory: 45 shared loads for 30 FMAs per
+// output, 370 us for the 0.97 M rows x 64 channels of the BASELINE batch against ~80 us of output traffic (sc fp32 +
+// operand planes), plus a separate 97 us fp32 -> planes pass.  Now: a lane owns a channel PAIR with the 60 weights in
+// registers, a warp walks the tile three rows at a time (25 broadcast sample loads for 180 FMAs) and the conv1 output
+// goes out as the next GEMM's operand planes directly.  The fmaf order per output (k = 0 .. 14, then the bias) is the
+// old kernel's, so results are unchanged bit for bit.
 // ---------------------------------------------------------------------------------------------------
-template <int KS>
-__global__ void __launch_bounds__(256) wav_stem_kernel(
+constexpr int STEM_ROWS = 192;            // rows per CTA
+constexpr int STEM_THREADS = 256;
+
+template <bool F16>
+__device__ __forceinline__ void stem_store_planes2(const PmPlanes& P, long long row, int c, float a, float b) {
+  if constexpr (F16) {
+    if (P.nsplit == 2) {                  // two fp16 planes: 4-byte stores, plane 0 by bit mask (pm_f16_head)
+      __half* o = reinterpret_cast<__half*>(P.ptr) + row * P.ld + c;
+      a *= PM_F16_ACT_SCALE; b *= PM_F16_ACT_SCALE;
+      const float a0 = pm_f16_head(a), b0 = pm_f16_head(b);
+      *reinterpret_cast<__half2*>(o) = __floats2half2_rn(a0, b0);
+      *reinterpret_cast<__half2*>(o + P.ps) = __floats2half2_rn(a - a0, b - b0);
+      return;
+    }
+  }
+  pm_store_planes_t<F16>(P, row, c, a);
+  pm_store_planes_t<F16>(P, row, c + 1, b);
+}
+
+template <int KS, int COUT, bool F16>
+__global__ void __launch_bounds__(STEM_THREADS, 2) wav_stem_kernel(
     const float* __restrict__ audio, long long a_bs, long long a_ws, int batch, int n_samples,
     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ wd,
-    const float* __restrict__ bd, int cout, int stride, int pad, int rows_out, float slope,
-    float* __restrict__ y1, float* __restrict__ sc) {
-  extern __shared__ float smem[];          // [2][cout][KS] weights, then the input span of this tile
-  const int rows_per_cta = 64;
-  float* sw1 = smem;
-  float* swd = smem + cout * KS;
-  float* sx = swd + cout * KS;             // (rows_per_cta-1)*stride + KS samples
+    const float* __restrict__ bd, int stride, int pad, int rows_out, float slope,
+    float* __restrict__ y1, float* __restrict__ sc, const PmPlanes P) {
+  extern __shared__ float sx[];            // the input span of this tile: (STEM_ROWS - 1) * stride + KS samples
+  constexpr int LPR = COUT / 2;            // lanes per row (a lane owns channels 2*cp, 2*cp + 1)
+  constexpr int RW = 32 / LPR;             // row groups per warp
+  constexpr int RPI = 3 * RW * (STEM_THREADS / 32);   // rows per CTA iteration
+  static_assert(STEM_ROWS % RPI == 0, "tile must be whole iterations");
   const int seq = blockIdx.y;              // w*batch + b: window-major, so one window's clips are contiguous
   const int w = seq / batch, b = seq % batch;
   const float* __restrict__ x = audio + (long long)b * a_bs + (long long)w * a_ws;
-  const int l0 = blockIdx.x * rows_per_cta;
-  const int span = (rows_per_cta - 1) * stride + KS;
-  for (int i = threadIdx.x; i < cout * KS; i += blockDim.x) { sw1[i] = w1[i]; swd[i] = wd[i]; }
-  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+  const int l0 = blockIdx.x * STEM_ROWS;
+  const int span = (STEM_ROWS - 1) * stride + KS;
+  for (int i = threadIdx.x; i < span; i += STEM_THREADS) {
     const int s = l0 * stride - pad + i;
     sx[i] = (s >= 0 && s < n_samples) ? x[s] : 0.f;
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < rows_per_cta * cout; idx += blockDim.x) {
-    const int r = idx / cout, co = idx % cout;
-    const int l = l0 + r;
-    if (l >= rows_out) break;
-    float a1 = 0.f, ad = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cp = lane % LPR, rs = lane / LPR;
+  const int c0 = 2 * cp;
+  float wa0[KS], wa1[KS], wb0[KS], wb1[KS];   // conv1 / downsample weights of the two channels
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const float xv = sx[r * stride + k];
-      a1 = fmaf(xv, sw1[co * KS + k], a1);
-      ad = fmaf(xv, swd[co * KS + k], ad);
+  for (int k = 0; k < KS; ++k) {
+    wa0[k] = __ldg(w1 + c0 * KS + k);
+    wa1[k] = __ldg(w1 + (c0 + 1) * KS + k);
+    wb0[k] = __ldg(wd + c0 * KS + k);
+    wb1[k] = __ldg(wd + (c0 + 1) * KS + k);
+  }
+  const float ba0 = __ldg(b1 + c0), ba1 = __ldg(b1 + c0 + 1), bb0 = __ldg(bd + c0), bb1 = __ldg(bd + c0 + 1);
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < STEM_ROWS / RPI; ++it) {
+    const int r0 = (it * (STEM_THREADS / 32) + warp) * 3 * RW + rs * 3;      // first of this lane's three rows (in tile)
+    if (l0 + r0 >= rows_out) continue;
+    const float* xr = sx + r0 * stride;
+    float acc[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    if (stride == 5) {                     // the reference's stem: rows share samples, 25 loads for three rows
+      float xv[2 * 5 + KS];
+#pragma unroll
+      for (int i = 0; i < 2 * 5 + KS; ++i) xv[i] = xr[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const float v = xv[5 * j + k];
+          acc[j][0] = fmaf(v, wa0[k], acc[j][0]);
+          acc[j][1] = fmaf(v, wa1[k], acc[j][1]);
+          acc[j][2] = fmaf(v, wb0[k], acc[j][2]);
+          acc[j][3] = fmaf(v, wb1[k], acc[j][3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const float v = xr[j * stride + k];
+          acc[j][0] = fmaf(v, wa0[k], acc[j][0]);
+          acc[j][1] = fmaf(v, wa1[k], acc[j][1]);
+          acc[j][2] = fmaf(v, wb0[k], acc[j][2]);
+          acc[j][3] = fmaf(v, wb1[k], acc[j][3]);
+        }
+      }
     }
-    a1 += b1[co];
-    ad += bd[co];
-    const long long o = ((long long)seq * rows_out + l) * cout + co;
-    y1[o] = a1 > 0.f ? a1 : a1 * slope;
-    sc[o] = ad;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int l = l0 + r0 + j;
+      if (l >= rows_out) break;
+      float a0 = acc[j][0] + ba0, a1 = acc[j][1] + ba1;
+      a0 = a0 > 0.f ? a0 : a0 * slope;
+      a1 = a1 > 0.f ? a1 : a1 * slope;
+      const long long row = (long long)seq * rows_out + l;
+      *reinterpret_cast<float2*>(sc + row * COUT + c0) = make_float2(acc[j][2] + bb0, acc[j][3] + bb1);
+      if (y1) *reinterpret_cast<float2*>(y1 + row * COUT + c0) = make_float2(a0, a1);
+      if (P.ptr) stem_store_planes2<F16>(P, row, c0, a0, a1);
+    }
   }
 }
 
@@ -184,17 +253,27 @@ inline int grid_for(long long work, int threads) {
 extern "C" int pm_wav_stem_f32(const float* audio, long long a_bs, long long a_ws, int batch, int windows,
                                int n_samples, const float* w1, const float* b1, const float* wd,
                                const float* bd, int cout, int ksize, int stride, int pad, int rows_out,
-                               float slope, float* y1, float* sc, void* stream) {
-  PM_REQUIRE(audio && w1 && b1 && wd && bd && y1 && sc);
+                               float slope, float* y1, float* sc,
+                               uint16_t* planes, long long p_ps, int p_ld, int p_nsplit, void* stream) {
+  PM_REQUIRE(audio && w1 && b1 && wd && bd && sc && (y1 || planes));
   PM_REQUIRE(batch > 0 && windows > 0 && n_samples > 0 && cout > 0 && stride > 0 && rows_out > 0);
-  if (ksize != 15) return PM_EUNSUPPORTED;
+  PM_TAKE_FMT(p_nsplit, f16);
+  PM_REQUIRE(pm_planes_ok(planes, p_ps, p_ld, p_nsplit, cout, false));
+  PM_REQUIRE(!planes || ((p_ld & 1) == 0 && (p_ps & 1) == 0 && (reinterpret_cast<uintptr_t>(planes) & 3) == 0));
+  PM_REQUIRE((reinterpret_cast<uintptr_t>(sc) & 7) == 0 && (!y1 || (reinterpret_cast<uintptr_t>(y1) & 7) == 0));
+  if (ksize != 15 || (cout != 32 && cout != 64)) return PM_EUNSUPPORTED;
   PM_REQUIRE((long long)batch * windows <= 65535);
-  const int span = 63 * stride + ksize;
-  const size_t smem = (size_t)(2 * cout * ksize + span) * sizeof(float);
+  const size_t smem = (size_t)((STEM_ROWS - 1) * stride + ksize) * sizeof(float);
   PM_REQUIRE(smem <= 48 * 1024);
-  dim3 grid(pm_cdiv(rows_out, 64), batch * windows);
-  wav_stem_kernel<15><<<grid, 256, smem, (cudaStream_t)stream>>>(
-      audio, a_bs, a_ws, batch, n_samples, w1, b1, wd, bd, cout, stride, pad, rows_out, slope, y1, sc);
+  const PmPlanes P{reinterpret_cast<__nv_bfloat16*>(planes), p_ps, p_ld, planes ? p_nsplit : 0};
+  dim3 grid(pm_cdiv(rows_out, STEM_ROWS), batch * windows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PM_STEM(CO, F)                                                                                          \
+  wav_stem_kernel<15, CO, F><<<grid, STEM_THREADS, smem, st>>>(audio, a_bs, a_ws, batch, n_samples, w1, b1, wd, bd, \
+                                                               stride, pad, rows_out, slope, y1, sc, P)
+  if (cout == 64) { if (f16) PM_STEM(64, true); else PM_STEM(64, false); }
+  else { if (f16) PM_STEM(32, true); else PM_STEM(32, false); }
+#undef PM_STEM
   PM_LAUNCH_CHECK();
 }
 

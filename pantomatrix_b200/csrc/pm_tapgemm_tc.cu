@@ -32,6 +32,7 @@ constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KB per plane
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
+constexpr int OCC2_SMEM_KB = 100;   // operand ring per CTA when two CTAs share an SM (2 x (100 + 1.2) KB < 227 KB)
 
 struct TcParams {
   int taps, pad, nsplit, kblocks;   // kblocks = ceil(cin / 64)
@@ -71,8 +72,13 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 // 64 KB into shared memory for 12 MMAs of 64 cycles - 83 B / cycle against the ~64 B / cycle an SM can take in from
 // L2, so the single-CTA mainloop is fill-bound (1 058 cycles per k-block instead of 768, profiles/r2/gemm_timeline_fp16.txt);
 // the pair needs 48 KB per CTA and k-block.
-template <int BN, bool F16, bool CG2>
-__global__ void __launch_bounds__(NUM_THREADS, 1) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+//
+// OCC = CTAs per SM the kernel is compiled for.  2 (64-column tiles only: 256 TMEM columns, 96 registers, half the operand
+// ring) is for launches of many short tiles - the WavEncoder's 64-channel convs: 7 552 tiles of 15 k-blocks, where one
+// resident CTA spent more time in prologue, pipeline fill and epilogue than in its mainloop (13 us per tile against
+// 5.7 us of operand fill, profiles/r2/launches_fp16x3.md); with two, one CTA's epilogue overlaps the other's mainloop.
+template <int BN, bool F16, bool CG2, int OCC = 1>
+__global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const TcParams p) {
   constexpr int W_ROWS_CTA = CG2 ? BN / 2 : BN;     // weight rows this CTA stages per k-block and plane
@@ -437,18 +443,19 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, bool F16, bool CG2>
+template <int BN, bool F16, bool CG2, int OCC = 1>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st, int pair_axis = 0) {
+  static_assert(OCC == 1 || (BN == 64 && !CG2), "two CTAs per SM: 64-column tiles only (TMEM columns, registers)");
   const int stage_bytes = p.nsplit * (A_TILE_BYTES + (CG2 ? BN / 2 : BN) * BK * 2);
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
-  int stages = (env_kb * 1024) / stage_bytes;
+  int stages = ((OCC == 2 ? OCC2_SMEM_KB : env_kb) * 1024) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return PM_EUNSUPPORTED;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
   static unsigned long long configured = 0;       // per template instantiation, one bit per device
   if (pm_first_use_on_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16, CG2, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { configured = 0; return (int)e; }
   }
   if constexpr (CG2) {                      // CTA pairs: 2-CTA clusters along the row-tile axis
@@ -464,10 +471,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     attr[0].val.clusterDim.z = pair_axis == 2 ? 2 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2>, ma, mw, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2, OCC>, ma, mw, p);
     return e == cudaSuccess ? PM_OK : (int)e;
   } else {
-    tapgemm_tc_kernel<BN, F16, CG2><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
+    tapgemm_tc_kernel<BN, F16, CG2, OCC><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
     PM_LAUNCH_CHECK();
   }
 }
@@ -550,11 +557,17 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   }
   dim3 grid(pm_cdiv(rows_out, R), pm_cdiv(cout, BNsel), pm_cdiv(batch, NB));
   PM_REQUIRE(grid.z <= 65535 && grid.y <= 65535);
+  // Two CTAs per SM for 64-column launches with more tiles than two per SM, if half the ring still holds 2 stages.
+  static const bool occ2_on = !(getenv("PM_TC_OCC2") && atoi(getenv("PM_TC_OCC2")) == 0);      // A/B switch (tools)
+  const bool occ2 = occ2_on && BNsel == 64 && (long long)grid.x * grid.y * grid.z > 2 * 148 &&
+                    OCC2_SMEM_KB * 1024 / (nsplit * (A_TILE_BYTES + 64 * BK * 2)) >= 2;
   if (f16) {
     if (cg2) return launch<128, true, true>(ma, mw, p, grid, (cudaStream_t)stream, pair_axis);
+    if (occ2) return launch<64, true, false, 2>(ma, mw, p, grid, (cudaStream_t)stream);
     if (BNsel == 64) return launch<64, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
     return launch<128, true, false>(ma, mw, p, grid, (cudaStream_t)stream);
   }
+  if (occ2) return launch<64, false, false, 2>(ma, mw, p, grid, (cudaStream_t)stream);
   if (BNsel == 64) return launch<64, false, false>(ma, mw, p, grid, (cudaStream_t)stream);
   return launch<128, false, false>(ma, mw, p, grid, (cudaStream_t)stream);
 }

@@ -333,7 +333,7 @@ class _WavEncoder:
         bs, n = audio.shape
         w1, b1, wd, bd, stride, pad = self.stem
         y, sc = ops.wav_stem(audio, n, a_ws, bs, windows, n_samples, w1, b1, wd, bd, stride=stride, pad=pad,
-                             slope=0.01, offset=offset)
+                             slope=0.01, offset=offset, nsplit=_ns())
         # block outputs feed the next block as (possibly strided) GEMM operand and as identity shortcut
         x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want="fp", out_slack=8)
         last = len(self.blocks) - 1

@@ -108,17 +108,23 @@ def tapgemm(a, w, bias, *, rows_out=None, stride=1, pad=0, act=ACT_NONE, slope=0
     return out
 
 
-def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0):
+def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0, nsplit=0):
     """First WavEncoder block's two convolutions on the raw waveform.  `audio` is the flat (bs, n)
-    tensor; sequence (b, w) starts at element offset + b*a_bs + w*a_ws and is n_samples long."""
+    tensor; sequence (b, w) starts at element offset + b*a_bs + w*a_ws and is n_samples long.
+    Returns (y1, sc): y1 as fp32 tensor (nsplit 0) or as the operand Planes of the conv that follows."""
     _chk(audio)
     cout, ks = w1.shape
     rows_out = (n_samples + 2 * pad - ks) // stride + 1
-    y1 = torch.empty(batch * windows, rows_out, cout, device=audio.device, dtype=torch.float32)
-    sc = torch.empty_like(y1)
+    sc = torch.empty(batch * windows, rows_out, cout, device=audio.device, dtype=torch.float32)
+    if nsplit:
+        y1 = _new_planes(nsplit, (batch * windows, rows_out), cout, audio.device)
+        y_ptr, pa = 0, (y1.t.data_ptr(), y1.t.stride(0), y1.t.stride(2), nsplit | _fmt_bit(y1.t))
+    else:
+        y1 = torch.empty_like(sc)
+        y_ptr, pa = y1.data_ptr(), (0, 0, 0, 0)
     _call("pm_wav_stem_f32", audio.data_ptr() + 4 * offset, a_bs, a_ws, batch, windows, n_samples,
           w1.data_ptr(), b1.data_ptr(), wd.data_ptr(), bd.data_ptr(), cout, ks, stride, pad, rows_out,
-          float(slope), y1.data_ptr(), sc.data_ptr(), _stream())
+          float(slope), y_ptr, sc.data_ptr(), *pa, _stream())
     return y1, sc
 
 

@@ -65,14 +65,15 @@ def tapgemm(a, w, bias, *, rows_out=None, stride=1, pad=0, act=ACT_NONE, slope=0
     return y.contiguous()
 
 
-def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0):
+def wav_stem(audio, a_bs, a_ws, batch, windows, n_samples, w1, b1, wd, bd, *, stride, pad, slope, offset=0, nsplit=0):
     flat = audio.reshape(-1)
     seqs = torch.stack([flat[offset + b * a_bs + w * a_ws: offset + b * a_bs + w * a_ws + n_samples]
                         for w in range(windows) for b in range(batch)])            # window-major
     x = seqs.unsqueeze(1)
     y1 = F.leaky_relu(F.conv1d(x, w1.unsqueeze(1), b1, stride=stride, padding=pad), slope).transpose(1, 2)
     sc = F.conv1d(x, wd.unsqueeze(1), bd, stride=stride, padding=pad).transpose(1, 2)
-    return y1.contiguous(), sc.contiguous()
+    y1 = y1.contiguous()
+    return (_mk_planes(y1, nsplit) if nsplit else y1), sc.contiguous()
 
 
 def add_layernorm(x, r, gamma, beta, eps=1e-5, nsplit=0, f32=True):

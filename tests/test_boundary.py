@@ -84,7 +84,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in pm_emage.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().pm_abi_version() == 4
+    assert _lib.load().pm_abi_version() == 5
 
 
 def test_ctypes_signatures_match_the_header():

@@ -87,17 +87,34 @@ def test_tapgemm_strided_views(ops):
 
 
 def test_wav_stem(ops):
-    bs, n, windows, ws, ns = 3, 9000, 2, 3000, 5863
+    bs, n, windows, ws, ns_ = 3, 9000, 2, 3000, 5863
     audio = _rand(bs, n, seed=11, scale=0.1)
     w1, wd = _rand(64, 15, seed=12, scale=0.5), _rand(64, 15, seed=13, scale=0.5)
     b1, bd = _rand(64, seed=14, scale=0.1), _rand(64, seed=15, scale=0.1)
-    y1, sc = ops.wav_stem(audio, n, ws, bs, windows, ns, w1, b1, wd, bd, stride=5, pad=1600, slope=0.01, offset=100)
+    y1, sc = ops.wav_stem(audio, n, ws, bs, windows, ns_, w1, b1, wd, bd, stride=5, pad=1600, slope=0.01, offset=100)
     for w in range(windows):
-        sl = audio[:, 100 + w * ws: 100 + w * ws + ns].double().unsqueeze(1)
+        sl = audio[:, 100 + w * ws: 100 + w * ws + ns_].double().unsqueeze(1)
         c1 = F.conv1d(sl, w1.double().unsqueeze(1), b1.double(), stride=5, padding=1600).transpose(1, 2)
         cd = F.conv1d(sl, wd.double().unsqueeze(1), bd.double(), stride=5, padding=1600).transpose(1, 2)
         _close(y1[w * bs:(w + 1) * bs], F.leaky_relu(c1, 0.01))          # window-major layout
         _close(sc[w * bs:(w + 1) * bs], cd)
+    # the tensor-core engines take conv1's output as operand planes straight from the stem: same values, split in-kernel
+    for ns, fmt in ((2, "fp16"), (3, "bf16"), (2, "bf16")):
+        old = ops.plane_format()
+        ops.set_plane_format(fmt)
+        try:
+            pl, sc2 = ops.wav_stem(audio, n, ws, bs, windows, ns_, w1, b1, wd, bd, stride=5, pad=1600, slope=0.01, offset=100, nsplit=ns)
+            ref = ops.split_bf16(y1, ns)
+            assert torch.equal(pl.t[..., :64], ref.t[..., :64]) and torch.equal(sc2, sc)
+        finally:
+            ops.set_plane_format(old)
+    # CaMN / DisCo stem width, stride != 5 through the generic path
+    w1s, wds, b1s, bds = w1[:32].contiguous(), wd[:32].contiguous(), b1[:32].contiguous(), bd[:32].contiguous()
+    for stride, pad in ((5, 1600), (4, 3)):
+        y, s_ = ops.wav_stem(audio, n, ws, bs, windows, ns_, w1s, b1s, wds, bds, stride=stride, pad=pad, slope=0.01)
+        sl = torch.cat([audio[:, w * ws: w * ws + ns_] for w in range(windows)]).double().unsqueeze(1)
+        _close(y, F.leaky_relu(F.conv1d(sl, w1s.double().unsqueeze(1), b1s.double(), stride=stride, padding=pad), 0.01).transpose(1, 2))
+        _close(s_, F.conv1d(sl, wds.double().unsqueeze(1), bds.double(), stride=stride, padding=pad).transpose(1, 2))
 
 
 @pytest.mark.parametrize("ch", [256, 768])
