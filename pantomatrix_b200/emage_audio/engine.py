@@ -334,13 +334,16 @@ class _WavEncoder:
         w1, b1, wd, bd, stride, pad = self.stem
         y, sc = ops.wav_stem(audio, n, a_ws, bs, windows, n_samples, w1, b1, wd, bd, stride=stride, pad=pad,
                              slope=0.01, offset=offset, nsplit=_ns())
-        # block outputs feed the next block as (possibly strided) GEMM operand and as identity shortcut
-        x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want="fp", out_slack=8)
+        # A block's output feeds the next block's convs as (possibly strided) GEMM operand - planes - and, only where
+        # that block has no downsample conv, as its identity shortcut - fp32.  (The first block's output is 0.25 GB
+        # per encoder in fp32 at the BASELINE batch: not writing it is the point.)
         last = len(self.blocks) - 1
+        form = lambda i: "f" if i == last else ("p" if self.blocks[i + 1][2] is not None else "fp")
+        x = self.blocks[0][1](y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want=form(0), out_slack=8)
         for i, (conv1, conv2, ds) in enumerate(self.blocks[1:], 1):
             y = conv1(x, act=ops.ACT_LEAKY, slope=0.01, want="p")
             sc = ds(x) if ds is not None else x
-            x = conv2(y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want="f" if i == last else "fp", out_slack=8)
+            x = conv2(y, act=ops.ACT_LEAKY, slope=0.01, residual=sc, want=form(i), out_slack=8)
         return x
 
 
