@@ -33,6 +33,8 @@ constexpr int A_TILE_BYTES = BM * BK * 2;           // 16 KB per plane
 constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int OCC2_SMEM_KB = 100;   // operand ring per CTA when two CTAs share an SM (2 x (100 + 1.2) KB < 227 KB)
+constexpr int HALO_ROWS = 144;      // halo mode: 128 output rows + up to 16 neighbours, whole 8-row swizzle groups
+constexpr int HALO_BYTES = HALO_ROWS * BK * 2;      // 18 KB per plane
 
 struct TcParams {
   int taps, pad, nsplit, kblocks;   // kblocks = ceil(cin / 64)
@@ -46,6 +48,7 @@ struct TcParams {
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
+  int halo_bo;       // halo mode: 1 = put the swizzle phase of the shifted start address into the descriptor's base offset
   float acc_scale;   // fp16 operands: weights are packed scaled by a power of two, undone here (1 for bf16)
 };
 
@@ -77,7 +80,14 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 // ring) is for launches of many short tiles - the WavEncoder's 64-channel convs: 7 552 tiles of 15 k-blocks, where one
 // resident CTA spent more time in prologue, pipeline fill and epilogue than in its mainloop (13 us per tile against
 // 5.7 us of operand fill, profiles/r2/launches_fp16x3.md); with two, one CTA's epilogue overlaps the other's mainloop.
-template <int BN, bool F16, bool CG2, int OCC = 1>
+//
+// HALO = one-k-block convs (cin <= 64) with several taps.  The tap-GEMM above re-stages the A tile for every tap although
+// consecutive taps read the same rows shifted by one: 15 x 32 KB of shared-memory fill per tile of the WavEncoder's
+// k = 15 convs, which made them fill-bound.  In halo mode the 128 + taps - 1 input rows of the tile are staged ONCE per
+// plane and tap t reads them through a descriptor whose start address is advanced by t rows (t x 128 B); a start that is
+// not 1024-byte aligned carries the swizzle phase in the descriptor's base-offset field ((start >> 7) & 7).  Only the
+// 8 KB W tiles stream through the ring.
+template <int BN, bool F16, bool CG2, int OCC = 1, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const TcParams p) {
@@ -97,12 +107,15 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][nsplit A tiles][nsplit W tiles] (1024-aligned), then barriers
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = p.nsplit * (A_TILE_BYTES + W_TILE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * stage_bytes);
+  // halo mode: [nsplit A halo planes][stages][nsplit W tiles]
+  const int stage_bytes = HALO ? p.nsplit * W_TILE_BYTES : p.nsplit * (A_TILE_BYTES + W_TILE_BYTES);
+  uint8_t* ring = HALO ? tiles + p.nsplit * HALO_BYTES : tiles;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;                       // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES]
   uint64_t* acc_bar = bars + 2 * MAX_STAGES;       // accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  uint64_t* halo_bar = bars + 2 * MAX_STAGES + 2;  // halo mode: A planes landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) PM_STAMP(0);                                   // kernel entry
@@ -120,6 +133,7 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(acc_bar), 1);
+    if constexpr (HALO) mbar_init(smem_u32(halo_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -155,7 +169,27 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.prefetch + off), "r"(n) : "memory");
       }
     }
-    {
+    if constexpr (HALO) {
+      if (elect_one()) {
+        mbar_expect_tx(smem_u32(halo_bar), (uint32_t)(p.nsplit * HALO_BYTES));
+        for (int pl = 0; pl < p.nsplit; ++pl)
+          tma_load_4d(smem_u32(tiles + pl * HALO_BYTES), &map_a, smem_u32(halo_bar), 0, l0 - p.pad, b0, pl);
+      }
+      __syncwarp();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_iter; ++it) {                      // one W tile pair per tap
+        mbar_wait_fast(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (elect_one()) {
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, (uint32_t)(p.nsplit * W_TILE_BYTES));
+          for (int pl = 0; pl < p.nsplit; ++pl)
+            tma_load_3d(smem_u32(ring + (size_t)s * stage_bytes + pl * W_TILE_BYTES), &map_w, bar, 0, it * p.w_rows + n0, pl);
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    } else {
       const uint32_t tx = (uint32_t)(p.nsplit * (A_TILE_BYTES + W_TILE_BYTES));
       int s = 0, tap = 0, kb = 0;
       uint32_t ph = 0;
@@ -209,7 +243,12 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
         else tc_commit(bar);
       };
       const uint32_t tiles_u32 = smem_u32(tiles);
+      const uint32_t ring_u32 = smem_u32(ring);
       const uint32_t d_corr = tmem_base + 2 * ACC;
+      if constexpr (HALO) {
+        mbar_wait_fast(smem_u32(halo_bar), 0);
+        tc_fence_after();
+      }
       uint32_t first_main0 = 1, first_main1 = 1, first_corr = 1;     // 1 until the accumulator has been written once
       int s = 0;
       uint32_t ph = 0;
@@ -218,10 +257,13 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
         tc_fence_after();
         if (it == 0) PM_STAMP(2);                                 // first operand stage landed
         if (elect_one()) {
-        const uint32_t a_base = tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
-        const uint64_t a0 = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFFu);                       // A plane 0, k = 0
-        const uint64_t w0 = desc_hi | (uint64_t)(((a_base + p.nsplit * A_TILE_BYTES) >> 4) & 0x3FFFu);
-        constexpr uint64_t A_PL = A_TILE_BYTES >> 4, W_PL = W_TILE_BYTES >> 4, K_ST = (UMMA_K * 2) >> 4;   // descriptor units
+        const uint32_t a_base = HALO ? tiles_u32 + (uint32_t)it * 128u                             // tap = row shift
+                                     : tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
+        const uint32_t w_base = HALO ? ring_u32 + (uint32_t)s * (uint32_t)stage_bytes : a_base + p.nsplit * A_TILE_BYTES;
+        // halo: the start address sits (it % 8) rows into a 1024-byte swizzle atom -> base offset field, bits 49-51
+        const uint64_t a0 = desc_hi | (HALO && p.halo_bo ? (uint64_t)((a_base >> 7) & 7u) << 49 : 0ull) | (uint64_t)((a_base >> 4) & 0x3FFFu);
+        const uint64_t w0 = desc_hi | (uint64_t)((w_base >> 4) & 0x3FFFu);
+        constexpr uint64_t A_PL = (HALO ? HALO_BYTES : A_TILE_BYTES) >> 4, W_PL = W_TILE_BYTES >> 4, K_ST = (UMMA_K * 2) >> 4;   // descriptor units
         const bool odd = it & 1;
         const uint32_t d_main = tmem_base + (odd ? ACC : 0);
         // cross products first (small -> large), into the correction accumulator
@@ -443,19 +485,21 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int BN, bool F16, bool CG2, int OCC = 1>
+template <int BN, bool F16, bool CG2, int OCC = 1, bool HALO = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid, cudaStream_t st, int pair_axis = 0) {
   static_assert(OCC == 1 || (BN == 64 && !CG2), "two CTAs per SM: 64-column tiles only (TMEM columns, registers)");
-  const int stage_bytes = p.nsplit * (A_TILE_BYTES + (CG2 ? BN / 2 : BN) * BK * 2);
+  static_assert(!HALO || (OCC == 2 && BN == 64), "halo mode is built for the 64-column, two-CTAs-per-SM form");
+  const int stage_bytes = HALO ? p.nsplit * BN * BK * 2 : p.nsplit * (A_TILE_BYTES + (CG2 ? BN / 2 : BN) * BK * 2);
+  const int fixed_bytes = HALO ? p.nsplit * HALO_BYTES : 0;
   static const int env_kb = getenv("PM_TC_SMEM_KB") ? atoi(getenv("PM_TC_SMEM_KB")) : 200;   // tuning override
-  int stages = ((OCC == 2 ? OCC2_SMEM_KB : env_kb) * 1024) / stage_bytes;
+  int stages = ((OCC == 2 ? OCC2_SMEM_KB : env_kb) * 1024 - fixed_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return PM_EUNSUPPORTED;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 2) * sizeof(uint64_t);
+  const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * MAX_STAGES + 3) * sizeof(uint64_t);
   static unsigned long long configured = 0;       // per template instantiation, one bit per device
   if (pm_first_use_on_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16, CG2, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, F16, CG2, OCC, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { configured = 0; return (int)e; }
   }
   if constexpr (CG2) {                      // CTA pairs: 2-CTA clusters along the row-tile axis
@@ -471,10 +515,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mw, TcParams& p, dim3 grid,
     attr[0].val.clusterDim.z = pair_axis == 2 ? 2 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2, OCC>, ma, mw, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_tc_kernel<BN, F16, CG2, OCC, HALO>, ma, mw, p);
     return e == cudaSuccess ? PM_OK : (int)e;
   } else {
-    tapgemm_tc_kernel<BN, F16, CG2, OCC><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
+    tapgemm_tc_kernel<BN, F16, CG2, OCC, HALO><<<grid, NUM_THREADS, smem, st>>>(ma, mw, p);
     PM_LAUNCH_CHECK();
   }
 }
@@ -527,6 +571,10 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   const bool cg2 = cg2_on && f16 && nsplit == 2 && BNsel == 128 && R == 128 && pm_cdiv(rows_out, R) % 2 == 0 &&
                    taps * ((cin + BK - 1) / BK) >= 6;
 
+  // Halo mode (see the kernel): one-k-block convs with >= 3 taps on 128-row tiles, two fp16 / bf16 planes.
+  static const int halo_mode = getenv("PM_TC_HALO") ? atoi(getenv("PM_TC_HALO")) : 0;      // 1: base offset set, 2: left 0
+  const bool halo = halo_mode != 0 && BNsel == 64 && R == 128 && cin <= BK && taps >= 3 && BM + taps - 1 <= HALO_ROWS && nsplit == 2;
+
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
   p.rows_out = rows_out; p.cout = cout; p.batch = batch; p.R = R; p.NB = NB; p.w_rows = w_rows;
@@ -539,13 +587,14 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.prefetch = static_cast<const uint8_t*>(prefetch);
   p.prefetch_bytes = prefetch ? prefetch_bytes : 0;
   p.acc_scale = acc_scale;
+  p.halo_bo = halo_mode == 1;
   CUtensorMap ma, mw;
   {
     const long long bs_el = batch > 1 ? a_bs : (long long)rows_in * lda;
     const long long ps_el = nsplit > 1 ? a_ps : bs_el * batch;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)rows_in, (cuuint64_t)batch, (cuuint64_t)nsplit};
     cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)bs_el * 2, (cuuint64_t)ps_el * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)R, (cuuint32_t)NB, 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(halo ? HALO_ROWS : R), (cuuint32_t)NB, 1};
     if (!encode_map(&ma, A, 4, dims, strides, box, f16)) return PM_EBADARG;
   }
   {
@@ -561,6 +610,10 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   static const bool occ2_on = !(getenv("PM_TC_OCC2") && atoi(getenv("PM_TC_OCC2")) == 0);      // A/B switch (tools)
   const bool occ2 = occ2_on && BNsel == 64 && (long long)grid.x * grid.y * grid.z > 2 * 148 &&
                     OCC2_SMEM_KB * 1024 / (nsplit * (A_TILE_BYTES + 64 * BK * 2)) >= 2;
+  if (halo) {
+    if (f16) return launch<64, true, false, 2, true>(ma, mw, p, grid, (cudaStream_t)stream);
+    return launch<64, false, false, 2, true>(ma, mw, p, grid, (cudaStream_t)stream);
+  }
   if (f16) {
     if (cg2) return launch<128, true, true>(ma, mw, p, grid, (cudaStream_t)stream, pair_axis);
     if (occ2) return launch<64, true, false, 2>(ma, mw, p, grid, (cudaStream_t)stream);
