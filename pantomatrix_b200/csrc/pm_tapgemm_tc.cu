@@ -48,7 +48,6 @@ struct TcParams {
   __nv_bfloat16* out_bf16; long long ob_ps, ob_bs; int ldob; int out_nsplit;
   int stages;
   const uint8_t* prefetch; long long prefetch_bytes;   // next GEMM's weights: pulled into L2 while this one runs
-  int halo_bo;       // halo mode: 1 = put the swizzle phase of the shifted start address into the descriptor's base offset
   float acc_scale;   // fp16 operands: weights are packed scaled by a power of two, undone here (1 for bf16)
 };
 
@@ -84,9 +83,11 @@ __device__ unsigned long long pm_tc_stamps[4096 * 8];
 // HALO = one-k-block convs (cin <= 64) with several taps.  The tap-GEMM above re-stages the A tile for every tap although
 // consecutive taps read the same rows shifted by one: 15 x 32 KB of shared-memory fill per tile of the WavEncoder's
 // k = 15 convs, which made them fill-bound.  In halo mode the 128 + taps - 1 input rows of the tile are staged ONCE per
-// plane and tap t reads them through a descriptor whose start address is advanced by t rows (t x 128 B); a start that is
-// not 1024-byte aligned carries the swizzle phase in the descriptor's base-offset field ((start >> 7) & 7).  Only the
-// 8 KB W tiles stream through the ring.
+// plane and tap t reads them through a descriptor whose start address is advanced by t rows (t x 128 B).  Measured on
+// B200 (profiles/r2/halo_mode_trial.md): the tensor core derives the 128B-swizzle phase from the ADDRESS bits 7-9, so a
+// start address that is not 1024-byte aligned needs nothing else - the descriptor's base-offset field must stay 0 (with
+// (start >> 7) & 7 in it, as the PTX text suggests for unaligned starts, every result was wrong).  Only the 8 KB W tiles
+// stream through the ring.  WavEncoder 64 -> 64, k = 15 conv over 0.97 M rows: 444 -> 420 us.
 template <int BN, bool F16, bool CG2, int OCC = 1, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_w,
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(NUM_THREADS, OCC) tapgemm_tc_kernel(const __gr
         const uint32_t a_base = HALO ? tiles_u32 + (uint32_t)it * 128u                             // tap = row shift
                                      : tiles_u32 + (uint32_t)s * (uint32_t)stage_bytes;
         const uint32_t w_base = HALO ? ring_u32 + (uint32_t)s * (uint32_t)stage_bytes : a_base + p.nsplit * A_TILE_BYTES;
-        // halo: the start address sits (it % 8) rows into a 1024-byte swizzle atom -> base offset field, bits 49-51
-        const uint64_t a0 = desc_hi | (HALO && p.halo_bo ? (uint64_t)((a_base >> 7) & 7u) << 49 : 0ull) | (uint64_t)((a_base >> 4) & 0x3FFFu);
+        // halo: the start address sits (it % 8) rows into a 1024-byte swizzle atom; base offset (bits 49-51) stays 0
+        const uint64_t a0 = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFFu);
         const uint64_t w0 = desc_hi | (uint64_t)((w_base >> 4) & 0x3FFFu);
         constexpr uint64_t A_PL = (HALO ? HALO_BYTES : A_TILE_BYTES) >> 4, W_PL = W_TILE_BYTES >> 4, K_ST = (UMMA_K * 2) >> 4;   // descriptor units
         const bool odd = it & 1;
@@ -572,8 +573,8 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
                    taps * ((cin + BK - 1) / BK) >= 6;
 
   // Halo mode (see the kernel): one-k-block convs with >= 3 taps on 128-row tiles, two fp16 / bf16 planes.
-  static const int halo_mode = getenv("PM_TC_HALO") ? atoi(getenv("PM_TC_HALO")) : 0;      // 1: base offset set, 2: left 0
-  const bool halo = halo_mode != 0 && BNsel == 64 && R == 128 && cin <= BK && taps >= 3 && BM + taps - 1 <= HALO_ROWS && nsplit == 2;
+  static const bool halo_on = !(getenv("PM_TC_HALO") && atoi(getenv("PM_TC_HALO")) == 0);      // A/B switch (tools)
+  const bool halo = halo_on && BNsel == 64 && R == 128 && cin <= BK && taps >= 3 && BM + taps - 1 <= HALO_ROWS && nsplit == 2;
 
   TcParams p;
   p.taps = taps; p.pad = pad; p.nsplit = nsplit; p.kblocks = (cin + BK - 1) / BK;
@@ -587,7 +588,6 @@ extern "C" int pm_tapgemm_tc(const uint16_t* A, long long a_ps, long long a_bs, 
   p.prefetch = static_cast<const uint8_t*>(prefetch);
   p.prefetch_bytes = prefetch ? prefetch_bytes : 0;
   p.acc_scale = acc_scale;
-  p.halo_bo = halo_mode == 1;
   CUtensorMap ma, mw;
   {
     const long long bs_el = batch > 1 ? a_bs : (long long)rows_in * lda;

@@ -1,5 +1,5 @@
-"""Halo-mode tap-GEMM (PM_TC_HALO=1|2, read once per process) against torch float64 convs: exit 0 when every case is
-within fp16x3 accuracy.  PM_TC_HALO=0 checks the default path with the same cases."""
+"""One-k-block, many-tap convs (the shapes the tap-GEMM's halo mode takes) against torch float64 convs: exit 0 when every
+case is within fp16x3 accuracy.  PM_TC_HALO=0 (read once per process) runs the same cases through the per-tap path."""
 import math
 import os
 import sys
