@@ -140,3 +140,21 @@ def test_fp16_planes_small_activations(ops, scale, tol):
         assert err <= tol * float(want.abs().max()), err
     finally:
         ops.set_plane_format("bf16")
+
+
+@pytest.mark.parametrize("halo", ["1", "0"])
+def test_halo_mode_and_per_tap_staging_agree_with_float64(halo):
+    """One-k-block, many-tap convs (the WavEncoder's 64-channel k = 15 convs) run in the tap-GEMM's halo mode by default:
+    the A rows are staged once and tap t reads them through a descriptor whose start address is shifted by t rows
+    (csrc/pm_tapgemm_tc.cu; hardware behaviour recorded in profiles/r2/halo_mode_trial.md).  PM_TC_HALO is read once per
+    process, so each staging mode gets its own interpreter; both must reproduce float64 convs to fp16x3 accuracy."""
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PM_TC_HALO=halo)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_halo.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(" ok") == 7, r.stdout
